@@ -1,0 +1,1143 @@
+// Host side of the B200 BLiM scoring engine + its C ABI (include/blim_b200.h).
+//
+// The host code here is the "scheduler" of SURVEY.md 7(6): it turns a list of (video, text) pairs into a few large
+// decoder runs so that every GEMM sees thousands of rows:
+//   * VTG      : per video one PREFIX sequence [system/user header | 64*n_clips projected visual rows | prompt tail]
+//                prefilled once into the prefix KV cache; every caption of that video is a SUFFIX sequence that attends
+//                to the cached prefix (cascade attention) -- replaces the per-pair 300-token prefill of
+//                compute_v2t_scores_x / compute_t2v_scores_x (reference retrieval_utils.py:62-97, 121-134).
+//   * VTG prior: the CPN mask hides the visual rows as keys (modeling_videochat_flash.py:433), so the prior only depends
+//                on the text: one shared prefix (header + prompt tail at gapped rotary positions), one suffix per text.
+//   * TVG      : prefix = text part of the TVG prompt (per text), suffix = the first n_clips-1 pooled visual rows.
+//   * TVG prior: prefix = the tvg_prefix_length visible header tokens (modeling_videochat_flash.py:414-417), suffix =
+//                [last text token, invisible as a key] + pooled visual rows; shared by all texts of equal length.
+// Scoring never materialises logits: LM head / TVG head run through the fused log-sum-exp GEMM epilogue.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/blim_b200.h"
+#include "attention.cuh"
+#include "gemm_sm100.cuh"
+#include "kernels_misc.cuh"
+
+using namespace blim;
+typedef __nv_bfloat16 bf16;
+
+static std::string g_create_error;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct LayerW {
+  DevBuf w_qkv, w_o, w_gu, w_down, b_qkv, ln1, ln2;
+};
+struct ProjW {
+  DevBuf w0, b0, w2, b2;
+};
+
+struct PromptGroup {
+  std::vector<int32_t> pre, post;  // prompt ids before / after the image sentinel (VTG), or the visible header (TVG prior)
+};
+struct TextTable {
+  int n = 0;
+  std::vector<int32_t> ids, labels;
+  std::vector<int64_t> off;
+  std::vector<int> img_pos;   // index of the -200 sentinel
+  std::vector<int> first_lab; // first index with label != -100 (VTG)
+  std::vector<int> group;     // prompt group of each text
+  std::vector<PromptGroup> groups;
+};
+
+// One flat decoder run: T tokens, S sequences.
+struct Run {
+  std::vector<int> tok_src, tok_pos;
+  std::vector<uint8_t> key_valid;
+  std::vector<AttnSeq> seqs;
+  bool any_invalid = false;
+  int T() const { return static_cast<int>(tok_src.size()); }
+  void clear() {
+    tok_src.clear(); tok_pos.clear(); key_valid.clear(); seqs.clear(); any_invalid = false;
+  }
+  // returns index of the first token
+  int begin_seq(int a_start, int a_len) {
+    AttnSeq s;
+    s.q_start = T(); s.q_len = 0; s.a_start = a_start; s.a_len = a_len; s.b_start = T();
+    seqs.push_back(s);
+    return s.q_start;
+  }
+  void push(int src, int pos, bool valid = true) {
+    tok_src.push_back(src); tok_pos.push_back(pos); key_valid.push_back(valid ? 1 : 0);
+    if (!valid) any_invalid = true;
+    seqs.back().q_len++;
+  }
+  void end_seq() {
+    if (seqs.back().q_len == 0) seqs.pop_back();
+  }
+};
+
+}  // namespace
+
+struct blim_engine {
+  blim_model_cfg cfg;
+  int device = 0;
+  std::string err;
+  GemmLaunchCtx gemm;
+  long long launches = 0;
+  double flops = 0.0;
+
+  int H, NL, NH, NKV, DH, I, V, MM, TPC, NQ, NKVD, NQKV, G;
+  int Tmax, Pmax, Umax;
+
+  // weights
+  DevBuf embed, lm_head, visual_head, norm;
+  std::vector<LayerW> layers;
+  ProjW proj[2];  // 0 = mlp (VTG), 1 = tvg_mlp
+  DevBuf rope_cos, rope_sin;
+  int rope_n = 0;
+  long long weights_loaded = 0;
+
+  // corpus
+  DevBuf feats;  // [n_videos, n_clips*TPC, MM] bf16
+  int n_videos = 0, n_clips = 0;
+  TextTable texts[2];
+  DevBuf vocab;  // [n_clips, n_vocab, MM] bf16
+  int n_vocab = 0;
+  std::vector<int32_t> video_labels;
+  int tvg_prefix_len = 21;
+  DevBuf tvg_vis;  // [n_videos * n_clips, H] bf16 pooled tvg_mlp rows
+  bool tvg_vis_ready = false;
+
+  // workspaces
+  DevBuf x, xn, q, attn, k_own, v_own, act, kp, vp, prefix_last, vis, proj_tmp, lm_a, pred, partial, tgt_logit, logp, uniq_scores;
+  DevBuf d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map;
+  size_t partial_tiles = 0;
+
+  int fail(const std::string& m) {
+    err = m;
+    return 1;
+  }
+  int fail_cuda(const char* what, cudaError_t e) {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return 1;
+  }
+};
+
+#define CKE(expr)                                                   \
+  do {                                                              \
+    cudaError_t _e = (expr);                                        \
+    if (_e != cudaSuccess) return e->fail_cuda(#expr, _e);          \
+  } while (0)
+#define CKL()                                                       \
+  do {                                                              \
+    e->launches++;                                                  \
+    cudaError_t _e = cudaGetLastError();                            \
+    if (_e != cudaSuccess) return e->fail_cuda("kernel launch", _e); \
+  } while (0)
+#define CKR(expr)                \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != 0) return _r;      \
+  } while (0)
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ------------------------------------------------------------------------------------------------ GEMM wrappers
+template <class Epi>
+static int gemm(blim_engine* e, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const typename Epi::Params& p,
+                cudaStream_t st) {
+  if (M <= 0) return 0;
+  cudaError_t r = launch_gemm<Epi>(e->gemm, A, lda, W, ldw, M, N, K, p, st);
+  if (r != cudaSuccess) return e->fail_cuda("tcgen05 gemm launch", r);
+  e->flops += 2.0 * M * static_cast<double>(N) * K;
+  return 0;
+}
+
+static int gemm_qkv(blim_engine* e, const bf16* A, const LayerW& w, int M, bf16* q_out, bf16* k_out, bf16* v_out, const int* pos,
+                    cudaStream_t st) {
+  if (e->DH == 128) {
+    EpiQkvRope<128>::Params p{q_out, k_out, v_out, w.b_qkv.as<float>(), pos, nullptr, e->rope_cos.as<float>(), e->rope_sin.as<float>(),
+                              e->NQ, e->NKVD};
+    return gemm<EpiQkvRope<128>>(e, A, e->H, w.w_qkv.as<bf16>(), e->H, M, e->NQKV, e->H, p, st);
+  }
+  EpiQkvRope<64>::Params p{q_out, k_out, v_out, w.b_qkv.as<float>(), pos, nullptr, e->rope_cos.as<float>(), e->rope_sin.as<float>(),
+                           e->NQ, e->NKVD};
+  return gemm<EpiQkvRope<64>>(e, A, e->H, w.w_qkv.as<bf16>(), e->H, M, e->NQKV, e->H, p, st);
+}
+
+// ------------------------------------------------------------------------------------------------ create / destroy
+extern "C" const char* blim_last_error(const blim_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+extern "C" void blim_destroy(blim_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  DevBuf* bufs[] = {&e->embed, &e->lm_head, &e->visual_head, &e->norm, &e->rope_cos, &e->rope_sin, &e->feats, &e->vocab, &e->tvg_vis,
+                    &e->x, &e->xn, &e->q, &e->attn, &e->k_own, &e->v_own, &e->act, &e->kp, &e->vp, &e->prefix_last, &e->vis,
+                    &e->proj_tmp, &e->lm_a, &e->pred, &e->partial, &e->tgt_logit, &e->logp, &e->uniq_scores, &e->d_tok_src,
+                    &e->d_tok_pos, &e->d_key_valid, &e->d_seqs, &e->d_works, &e->d_idx, &e->d_targets, &e->d_row_off, &e->d_map};
+  for (DevBuf* b : bufs) b->release();
+  for (LayerW& l : e->layers) {
+    l.w_qkv.release(); l.w_o.release(); l.w_gu.release(); l.w_down.release(); l.b_qkv.release(); l.ln1.release(); l.ln2.release();
+  }
+  for (ProjW& p : e->proj) { p.w0.release(); p.b0.release(); p.w2.release(); p.b2.release(); }
+  delete e;
+}
+
+extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return 1; }
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n_dev);
+  if (ce != cudaSuccess || n_dev <= 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(ce) + " (the engine has no CPU fallback)";
+    return 1;
+  }
+  if ((ce = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(ce); return 1; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_error = "blim_b200 needs an sm_100a device (got sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")";
+    return 1;
+  }
+  blim_engine* e = new blim_engine();
+  e->cfg = *cfg;
+  e->device = device;
+  e->H = cfg->hidden_size; e->NL = cfg->num_layers; e->NH = cfg->num_heads; e->NKV = cfg->num_kv_heads; e->DH = cfg->head_dim;
+  e->I = cfg->intermediate_size; e->V = cfg->vocab_size; e->MM = cfg->mm_hidden_size; e->TPC = cfg->tokens_per_clip;
+  e->NQ = e->NH * e->DH; e->NKVD = e->NKV * e->DH; e->NQKV = e->NQ + 2 * e->NKVD;
+  e->G = e->NKV > 0 ? e->NH / e->NKV : 0;
+  e->Tmax = cfg->max_run_tokens > 0 ? cfg->max_run_tokens : 32768;
+  e->Pmax = cfg->max_prefix_tokens > 0 ? cfg->max_prefix_tokens : 32768;
+  e->Umax = std::min(e->Pmax, 8192);
+  e->gemm.num_sms = prop.multiProcessorCount;
+  e->gemm.cta_group = cfg->gemm_cta_group == 2 ? 2 : 1;
+  auto bad = [&](const char* m) {
+    g_create_error = m;
+    delete e;
+    return 1;
+  };
+  if (e->DH != 64 && e->DH != 128) return bad("head_dim must be 64 or 128");
+  if (e->NKV <= 0 || e->NH % e->NKV) return bad("num_heads must be a multiple of num_kv_heads");
+  if (e->H % 64 || e->NQ % 64 || e->I % 128 || e->MM % 64) return bad("hidden/intermediate/mm sizes must be multiples of 64/128/64");
+  if (e->H % 8 || e->NQ != e->H) return bad("num_heads*head_dim must equal hidden_size");
+  if (kBN % e->DH) return bad("head_dim must divide 256");
+  if (cfg->max_positions <= 0) return bad("max_positions must be > 0");
+
+  const size_t T = e->Tmax, P = e->Pmax;
+  e->layers.resize(e->NL);
+  struct { DevBuf* b; size_t bytes; } allocs[] = {
+      {&e->x, T * e->H * 4}, {&e->xn, T * e->H * 2}, {&e->q, T * e->NQ * 2}, {&e->attn, T * e->NQ * 2},
+      {&e->k_own, T * e->NKVD * 2}, {&e->v_own, T * e->NKVD * 2}, {&e->act, T * static_cast<size_t>(e->I) * 2},
+      {&e->kp, static_cast<size_t>(e->NL) * P * e->NKVD * 2}, {&e->vp, static_cast<size_t>(e->NL) * P * e->NKVD * 2},
+      {&e->prefix_last, static_cast<size_t>(e->Umax) * e->H * 4}, {&e->vis, P * e->H * 2}, {&e->proj_tmp, T * e->H * 2},
+      {&e->lm_a, T * e->H * 2}, {&e->pred, T * e->MM * 2}, {&e->tgt_logit, T * 4}, {&e->logp, T * 4},
+      {&e->d_tok_src, T * 4}, {&e->d_tok_pos, T * 4}, {&e->d_key_valid, T}, {&e->d_seqs, T * sizeof(AttnSeq)},
+      {&e->d_works, (T * e->G / kAttnRows + T + 1) * sizeof(AttnWork)}, {&e->d_idx, T * 4}, {&e->d_targets, T * 4},
+      {&e->d_row_off, (T + 1) * 4}};
+  for (auto& a : allocs) {
+    cudaError_t r = a.b->reserve(a.bytes);
+    if (r != cudaSuccess) {
+      g_create_error = std::string("workspace allocation failed: ") + cudaGetErrorString(r);
+      blim_destroy(e);
+      return 1;
+    }
+  }
+  *out = e;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+static int repack_bf16(blim_engine* e, DevBuf& dst, size_t dst_rows, const void* src, int dtype, int rows, int cols, int dst_row0,
+                       int interleave, int half, cudaStream_t st) {
+  CKE(dst.reserve(dst_rows * cols * 2));
+  const size_t n = static_cast<size_t>(rows) * cols;
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
+  repack_rows_bf16_kernel<<<blocks, 256, 0, st>>>(dst.as<bf16>(), src, dtype, rows, cols, dst_row0, interleave, half);
+  CKL();
+  return 0;
+}
+static int repack_f32(blim_engine* e, DevBuf& dst, size_t dst_elems, size_t dst_off, const void* src, int dtype, size_t n, int round_bf16,
+                      cudaStream_t st) {
+  CKE(dst.reserve(dst_elems * 4));
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
+  repack_f32_kernel<<<blocks, 256, 0, st>>>(dst.as<float>() + dst_off, src, dtype, n, round_bf16);
+  CKL();
+  return 0;
+}
+
+extern "C" int blim_load_weight(blim_engine* e, const char* name_c, const void* src, int dtype, const int64_t* shape, int ndim, void* stream) {
+  if (!e || !name_c || !src) return e ? e->fail("null argument") : 1;
+  if (dtype < 0 || dtype > 2) return e->fail("bad dtype");
+  CKE(cudaSetDevice(e->device));
+  cudaStream_t st = S(stream);
+  const std::string name(name_c);
+  auto is2 = [&](int64_t r, int64_t c) { return ndim == 2 && shape[0] == r && shape[1] == c; };
+  auto is1 = [&](int64_t n) { return ndim == 1 && shape[0] == n; };
+  auto shape_err = [&]() { return e->fail("unexpected shape for " + name); };
+  const int H = e->H, I = e->I, V = e->V, MM = e->MM, NQ = e->NQ, NKVD = e->NKVD, NQKV = e->NQKV;
+  e->tvg_vis_ready = false;
+  e->weights_loaded++;
+  if (name == "model.embed_tokens.weight") {
+    if (!is2(V, H)) return shape_err();
+    return repack_bf16(e, e->embed, V, src, dtype, V, H, 0, 0, 0, st);
+  }
+  if (name == "lm_head.weight") {
+    if (!is2(V, H)) return shape_err();
+    return repack_bf16(e, e->lm_head, V, src, dtype, V, H, 0, 0, 0, st);
+  }
+  if (name == "visual_head.weight") {
+    if (!is2(MM, H)) return shape_err();
+    return repack_bf16(e, e->visual_head, MM, src, dtype, MM, H, 0, 0, 0, st);
+  }
+  if (name == "model.norm.weight") {
+    if (!is1(H)) return shape_err();
+    return repack_f32(e, e->norm, H, 0, src, dtype, H, 1, st);
+  }
+  const std::string pj = "model.mm_projector.";
+  if (name.compare(0, pj.size(), pj) == 0) {
+    std::string rest = name.substr(pj.size());
+    int which;
+    if (rest.compare(0, 4, "mlp.") == 0) { which = 0; rest = rest.substr(4); }
+    else if (rest.compare(0, 8, "tvg_mlp.") == 0) { which = 1; rest = rest.substr(8); }
+    else { e->weights_loaded--; return 2; }
+    ProjW& p = e->proj[which];
+    if (rest == "0.weight") { if (!is2(H, MM)) return shape_err(); return repack_bf16(e, p.w0, H, src, dtype, H, MM, 0, 0, 0, st); }
+    if (rest == "0.bias") { if (!is1(H)) return shape_err(); return repack_f32(e, p.b0, H, 0, src, dtype, H, 1, st); }
+    if (rest == "2.weight") { if (!is2(H, H)) return shape_err(); return repack_bf16(e, p.w2, H, src, dtype, H, H, 0, 0, 0, st); }
+    if (rest == "2.bias") { if (!is1(H)) return shape_err(); return repack_f32(e, p.b2, H, 0, src, dtype, H, 1, st); }
+    e->weights_loaded--;
+    return 2;
+  }
+  const std::string ly = "model.layers.";
+  if (name.compare(0, ly.size(), ly) == 0) {
+    size_t dot = name.find('.', ly.size());
+    if (dot == std::string::npos) { e->weights_loaded--; return 2; }
+    const int li = atoi(name.substr(ly.size(), dot - ly.size()).c_str());
+    if (li < 0 || li >= e->NL) return e->fail("layer index out of range: " + name);
+    LayerW& w = e->layers[li];
+    const std::string rest = name.substr(dot + 1);
+    if (rest == "self_attn.q_proj.weight") { if (!is2(NQ, H)) return shape_err(); return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NQ, H, 0, 0, 0, st); }
+    if (rest == "self_attn.k_proj.weight") { if (!is2(NKVD, H)) return shape_err(); return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NKVD, H, NQ, 0, 0, st); }
+    if (rest == "self_attn.v_proj.weight") { if (!is2(NKVD, H)) return shape_err(); return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NKVD, H, NQ + NKVD, 0, 0, st); }
+    if (rest == "self_attn.q_proj.bias") { if (!is1(NQ)) return shape_err(); return repack_f32(e, w.b_qkv, NQKV, 0, src, dtype, NQ, 1, st); }
+    if (rest == "self_attn.k_proj.bias") { if (!is1(NKVD)) return shape_err(); return repack_f32(e, w.b_qkv, NQKV, NQ, src, dtype, NKVD, 1, st); }
+    if (rest == "self_attn.v_proj.bias") { if (!is1(NKVD)) return shape_err(); return repack_f32(e, w.b_qkv, NQKV, NQ + NKVD, src, dtype, NKVD, 1, st); }
+    if (rest == "self_attn.o_proj.weight") { if (!is2(H, NQ)) return shape_err(); return repack_bf16(e, w.w_o, H, src, dtype, H, NQ, 0, 0, 0, st); }
+    if (rest == "mlp.gate_proj.weight") { if (!is2(I, H)) return shape_err(); return repack_bf16(e, w.w_gu, 2 * static_cast<size_t>(I), src, dtype, I, H, 0, 128, 0, st); }
+    if (rest == "mlp.up_proj.weight") { if (!is2(I, H)) return shape_err(); return repack_bf16(e, w.w_gu, 2 * static_cast<size_t>(I), src, dtype, I, H, 0, 128, 1, st); }
+    if (rest == "mlp.down_proj.weight") { if (!is2(H, I)) return shape_err(); return repack_bf16(e, w.w_down, H, src, dtype, H, I, 0, 0, 0, st); }
+    if (rest == "input_layernorm.weight") { if (!is1(H)) return shape_err(); return repack_f32(e, w.ln1, H, 0, src, dtype, H, 1, st); }
+    if (rest == "post_attention_layernorm.weight") { if (!is1(H)) return shape_err(); return repack_f32(e, w.ln2, H, 0, src, dtype, H, 1, st); }
+  }
+  e->weights_loaded--;
+  return 2;  // not a parameter of the scoring path (vision tower, rotary buffers, ...): ignored
+}
+
+extern "C" int blim_set_rope(blim_engine* e, const float* cos_dev, const float* sin_dev, int n_positions, void* stream) {
+  if (!e || !cos_dev || !sin_dev || n_positions <= 0) return e ? e->fail("bad rope arguments") : 1;
+  CKE(cudaSetDevice(e->device));
+  const size_t bytes = static_cast<size_t>(n_positions) * (e->DH / 2) * 4;
+  CKE(e->rope_cos.reserve(bytes));
+  CKE(e->rope_sin.reserve(bytes));
+  CKE(cudaMemcpyAsync(e->rope_cos.p, cos_dev, bytes, cudaMemcpyDeviceToDevice, S(stream)));
+  CKE(cudaMemcpyAsync(e->rope_sin.p, sin_dev, bytes, cudaMemcpyDeviceToDevice, S(stream)));
+  e->rope_n = n_positions;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ corpus
+extern "C" int blim_set_videos(blim_engine* e, const void* feats_dev, int dtype, int n_videos, int n_clips, void* stream) {
+  if (!e || !feats_dev || n_videos <= 0 || n_clips <= 0) return e ? e->fail("bad video arguments") : 1;
+  CKE(cudaSetDevice(e->device));
+  const int rows = n_videos * n_clips * e->TPC;
+  CKR(repack_bf16(e, e->feats, rows, feats_dev, dtype, rows, e->MM, 0, 0, 0, S(stream)));
+  e->n_videos = n_videos;
+  e->n_clips = n_clips;
+  e->tvg_vis_ready = false;
+  return 0;
+}
+
+extern "C" int blim_set_texts(blim_engine* e, int which, const int32_t* ids, const int32_t* labels, const int64_t* off, int n_texts) {
+  if (!e || which < 0 || which > 1 || !ids || !labels || !off || n_texts <= 0) return e ? e->fail("bad text arguments") : 1;
+  TextTable& t = e->texts[which];
+  t = TextTable();
+  t.n = n_texts;
+  t.off.assign(off, off + n_texts + 1);
+  t.ids.assign(ids, ids + off[n_texts]);
+  t.labels.assign(labels, labels + off[n_texts]);
+  t.img_pos.resize(n_texts);
+  t.first_lab.resize(n_texts);
+  t.group.resize(n_texts);
+  std::map<std::vector<int32_t>, int> groups;
+  for (int i = 0; i < n_texts; ++i) {
+    const int64_t b = off[i], n = off[i + 1] - off[i];
+    int img = -1, n_img = 0, fl = static_cast<int>(n);
+    for (int64_t j = 0; j < n; ++j) {
+      if (ids[b + j] == -200) { if (img < 0) img = static_cast<int>(j); n_img++; }
+      else if (ids[b + j] < 0 || ids[b + j] >= e->V) return e->fail("token id out of range in text " + std::to_string(i));
+    }
+    for (int64_t j = 0; j < n; ++j)
+      if (labels[b + j] != -100) { fl = static_cast<int>(j); break; }
+    if (n_img != 1) return e->fail("text " + std::to_string(i) + " must contain exactly one image sentinel (-200)");
+    t.img_pos[i] = img;
+    t.first_lab[i] = fl;
+    if (which == BLIM_TEXTS_VTG) {
+      // scored tail must be contiguous, lie after the image and hold valid targets (base_dataset.py:80-81)
+      if (fl <= img) return e->fail("VTG text " + std::to_string(i) + ": labels start before the image token");
+      if (fl >= n) return e->fail("VTG text " + std::to_string(i) + ": nothing to score");
+      for (int64_t j = fl; j < n; ++j)
+        if (labels[b + j] < 0 || labels[b + j] >= e->V) return e->fail("VTG text " + std::to_string(i) + ": non-contiguous labels");
+    } else {
+      if (img < 1) return e->fail("TVG text " + std::to_string(i) + ": no text before the image token");
+    }
+    // prompt group: VTG = everything before the first scored token; TVG = the CPN-visible header
+    std::vector<int32_t> key;
+    if (which == BLIM_TEXTS_VTG) key.assign(ids + b, ids + b + fl);
+    auto it = groups.find(key);
+    if (which == BLIM_TEXTS_VTG) {
+      if (it == groups.end()) {
+        PromptGroup g;
+        g.pre.assign(ids + b, ids + b + img);
+        g.post.assign(ids + b + img + 1, ids + b + fl);
+        t.groups.push_back(g);
+        it = groups.emplace(key, static_cast<int>(t.groups.size()) - 1).first;
+      }
+      t.group[i] = it->second;
+    } else {
+      t.group[i] = 0;  // TVG prior groups depend on tvg_prefix_len: resolved at scoring time
+    }
+  }
+  return 0;
+}
+
+extern "C" int blim_set_video_vocab(blim_engine* e, const void* vocab_dev, int dtype, int n_vocab, const int32_t* labels, int n_videos,
+                                    void* stream) {
+  if (!e || !vocab_dev || n_vocab <= 0 || !labels || n_videos <= 0) return e ? e->fail("bad vocab arguments") : 1;
+  if (e->n_clips <= 0) return e->fail("call blim_set_videos before blim_set_video_vocab");
+  CKE(cudaSetDevice(e->device));
+  const size_t n = static_cast<size_t>(n_vocab) * e->n_clips * e->MM;
+  CKE(e->vocab.reserve(n * 2));
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
+  repack_vocab_kernel<<<blocks, 256, 0, S(stream)>>>(e->vocab.as<bf16>(), vocab_dev, dtype, n_vocab, e->n_clips, e->MM);
+  CKL();
+  e->n_vocab = n_vocab;
+  e->video_labels.assign(labels, labels + n_videos);
+  for (int v = 0; v < n_videos; ++v)
+    if (labels[v] < 0 || labels[v] >= n_vocab) return e->fail("video label out of range");
+  return 0;
+}
+
+extern "C" int blim_set_tvg_prefix_length(blim_engine* e, int n) {
+  if (!e || n < 0) return e ? e->fail("bad tvg prefix length") : 1;
+  e->tvg_prefix_len = n;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ building blocks
+static int check_ready(blim_engine* e) {
+  if (!e->embed.p || !e->lm_head.p || !e->norm.p) return e->fail("weights not loaded (embed_tokens / lm_head / norm)");
+  for (int l = 0; l < e->NL; ++l) {
+    const LayerW& w = e->layers[l];
+    if (!w.w_qkv.p || !w.w_o.p || !w.w_gu.p || !w.w_down.p || !w.b_qkv.p || !w.ln1.p || !w.ln2.p)
+      return e->fail("weights of layer " + std::to_string(l) + " not loaded");
+  }
+  if (!e->rope_cos.p) return e->fail("rotary table not set (blim_set_rope)");
+  return 0;
+}
+
+static int upload(blim_engine* e, DevBuf& dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return 0;
+  CKE(dst.reserve(bytes));
+  CKE(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, st));  // pageable source: staged before return
+  return 0;
+}
+
+static int rmsnorm(blim_engine* e, bf16* out, const float* x0, const float* x1, const int* idx, const float* w, int R, cudaStream_t st) {
+  if (R <= 0) return 0;
+  rmsnorm_kernel<<<R, 256, 0, st>>>(out, x0, x1, idx, w, R, e->H, e->cfg.rms_norm_eps);
+  CKL();
+  return 0;
+}
+
+// Projector MLP over `rows` feature rows: Linear -> GELU -> Linear (mm_projector_builder.py:156-159).
+static int project(blim_engine* e, const bf16* feats, int rows, int which, bf16* out, cudaStream_t st) {
+  const ProjW& p = e->proj[which];
+  if (!p.w0.p || !p.b0.p || !p.w2.p || !p.b2.p) return e->fail(which ? "tvg_mlp weights not loaded" : "mm_projector.mlp weights not loaded");
+  for (int r0 = 0; r0 < rows; r0 += e->Tmax) {
+    const int n = std::min(e->Tmax, rows - r0);
+    EpiStore<bf16, true, true>::Params p1{e->proj_tmp.as<bf16>(), e->H, p.b0.as<float>()};
+    CKR((gemm<EpiStore<bf16, true, true>>(e, feats + static_cast<size_t>(r0) * e->MM, e->MM, p.w0.as<bf16>(), e->MM, n, e->H, e->MM, p1, st)));
+    EpiStore<bf16, true, false>::Params p2{out + static_cast<size_t>(r0) * e->H, e->H, p.b2.as<float>()};
+    CKR((gemm<EpiStore<bf16, true, false>>(e, e->proj_tmp.as<bf16>(), e->H, p.w2.as<bf16>(), e->H, n, e->H, e->H, p2, st)));
+  }
+  return 0;
+}
+
+// Run the decoder over a flat token list.  x must already hold the input embeddings when `assembled` is true.
+static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool assembled, cudaStream_t st) {
+  const int T = run.T();
+  if (T == 0) return 0;
+  if (T > e->Tmax) return e->fail("internal: run exceeds max_run_tokens");
+  if (to_prefix_cache && T > e->Pmax) return e->fail("internal: prefix run exceeds max_prefix_tokens");
+  for (int p : run.tok_pos)
+    if (p < 0 || p >= e->rope_n) return e->fail("sequence longer than the rotary table (max_positions)");
+  std::vector<AttnWork> works;
+  for (size_t s = 0; s < run.seqs.size(); ++s) {
+    const int nb = (run.seqs[s].q_len * e->G + kAttnRows - 1) / kAttnRows;
+    for (int b = 0; b < nb; ++b) works.push_back(AttnWork{static_cast<int>(s), b});
+  }
+  CKR(upload(e, e->d_tok_pos, run.tok_pos.data(), T * sizeof(int), st));
+  CKR(upload(e, e->d_seqs, run.seqs.data(), run.seqs.size() * sizeof(AttnSeq), st));
+  CKR(upload(e, e->d_works, works.data(), works.size() * sizeof(AttnWork), st));
+  if (run.any_invalid) CKR(upload(e, e->d_key_valid, run.key_valid.data(), T, st));
+  if (!assembled) {
+    CKR(upload(e, e->d_tok_src, run.tok_src.data(), T * sizeof(int), st));
+    assemble_tokens_kernel<<<T, 128, 0, st>>>(e->x.as<float>(), e->embed.as<bf16>(), e->vis.as<bf16>(), e->d_tok_src.as<int>(), T, e->H);
+    CKL();
+  }
+  const size_t kv_layer = static_cast<size_t>(e->Pmax) * e->NKVD;
+  for (int l = 0; l < e->NL; ++l) {
+    const LayerW& w = e->layers[l];
+    bf16* kpl = e->kp.as<bf16>() + l * kv_layer;
+    bf16* vpl = e->vp.as<bf16>() + l * kv_layer;
+    bf16* k_out = to_prefix_cache ? kpl : e->k_own.as<bf16>();
+    bf16* v_out = to_prefix_cache ? vpl : e->v_own.as<bf16>();
+    CKR(rmsnorm(e, e->xn.as<bf16>(), e->x.as<float>(), nullptr, nullptr, w.ln1.as<float>(), T, st));
+    CKR(gemm_qkv(e, e->xn.as<bf16>(), w, T, e->q.as<bf16>(), k_out, v_out, e->d_tok_pos.as<int>(), st));
+    AttnParams ap;
+    ap.q = e->q.as<bf16>(); ap.o = e->attn.as<bf16>();
+    ap.k_a = kpl; ap.v_a = vpl; ap.k_b = k_out; ap.v_b = v_out;
+    ap.key_valid = run.any_invalid ? e->d_key_valid.as<uint8_t>() : nullptr;
+    ap.seqs = e->d_seqs.as<AttnSeq>(); ap.works = e->d_works.as<AttnWork>();
+    ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G;
+    ap.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(e->DH));
+    cudaError_t r = launch_attention(ap, static_cast<int>(works.size()), e->NKV, e->DH, st);
+    if (r != cudaSuccess) return e->fail_cuda("attention launch", r);
+    e->launches++;
+    e->flops += 0.0;  // attention FLOPs are accounted analytically by bench.py
+    EpiResid::Params pr{e->x.as<float>(), e->H};
+    CKR(gemm<EpiResid>(e, e->attn.as<bf16>(), e->NQ, w.w_o.as<bf16>(), e->NQ, T, e->H, e->NQ, pr, st));
+    CKR(rmsnorm(e, e->xn.as<bf16>(), e->x.as<float>(), nullptr, nullptr, w.ln2.as<float>(), T, st));
+    EpiSwiglu::Params ps{e->act.as<bf16>(), e->I};
+    CKR(gemm<EpiSwiglu>(e, e->xn.as<bf16>(), e->H, w.w_gu.as<bf16>(), e->H, T, 2 * e->I, e->H, ps, st));
+    CKR(gemm<EpiResid>(e, e->act.as<bf16>(), e->I, w.w_down.as<bf16>(), e->I, T, e->H, e->I, pr, st));
+  }
+  return 0;
+}
+
+// logp[r] = log softmax(scale * A[r] · W^T)[target[r]] for R rows, never materialising the logits.
+static int lse_rows(blim_engine* e, const bf16* A, int lda, const bf16* W, int ldw, int R, int N, int K, const int* targets_dev, float scale,
+                    float* logp_dev, cudaStream_t st) {
+  if (R <= 0) return 0;
+  const int n_tiles = (N + kBN - 1) / kBN;
+  CKE(e->partial.reserve(static_cast<size_t>(e->Tmax) * n_tiles * sizeof(float2)));
+  EpiLse::Params p{e->partial.as<float2>(), e->tgt_logit.as<float>(), targets_dev, scale};
+  CKR(gemm<EpiLse>(e, A, lda, W, ldw, R, N, K, p, st));
+  lse_finalize_kernel<<<(R + 7) / 8, 256, 0, st>>>(logp_dev, e->partial.as<float2>(), e->tgt_logit.as<float>(), R, n_tiles);
+  CKL();
+  return 0;
+}
+
+static int save_prefix_last(blim_engine* e, const std::vector<int>& last_tok, cudaStream_t st) {
+  const int U = static_cast<int>(last_tok.size());
+  if (U == 0) return 0;
+  CKR(upload(e, e->d_idx, last_tok.data(), U * sizeof(int), st));
+  gather_rows_f32_kernel<<<U, 256, 0, st>>>(e->prefix_last.as<float>(), e->x.as<float>(), e->d_idx.as<int>(), U, e->H);
+  CKL();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ batch planner
+struct Item {
+  int unit;     // owning unit
+  int suf_len;  // suffix tokens this item runs through the decoder
+  int key;      // unique-key index (result slot)
+};
+struct UnitPlan {
+  int prefix_len;
+  std::vector<int> items;  // indices into the item array
+};
+struct BatchUnit {
+  int unit;
+  int item_begin, item_end;  // range inside units[unit].items
+};
+
+static int plan_batches(blim_engine* e, const std::vector<UnitPlan>& units, const std::vector<Item>& items, int max_items,
+                        std::vector<std::vector<BatchUnit>>& batches) {
+  batches.clear();
+  std::vector<BatchUnit> cur;
+  long long cp = 0, cs = 0;
+  int ci = 0;
+  auto flush = [&]() {
+    if (!cur.empty()) batches.push_back(cur);
+    cur.clear(); cp = 0; cs = 0; ci = 0;
+  };
+  for (size_t u = 0; u < units.size(); ++u) {
+    const UnitPlan& up = units[u];
+    if (up.prefix_len > e->Pmax || up.prefix_len > e->Tmax) return e->fail("a prefix sequence exceeds the workspace (raise max_prefix_tokens / max_run_tokens)");
+    size_t pos = 0;
+    while (pos < up.items.size()) {
+      const int first_len = items[up.items[pos]].suf_len;
+      if (first_len > e->Tmax) return e->fail("a suffix sequence exceeds max_run_tokens");
+      if (cp + up.prefix_len > e->Pmax || static_cast<int>(cur.size()) + 1 > e->Umax || cs + first_len > e->Tmax || ci + 1 > max_items) flush();
+      BatchUnit bu{static_cast<int>(u), static_cast<int>(pos), static_cast<int>(pos)};
+      cp += up.prefix_len;
+      while (pos < up.items.size() && cs + items[up.items[pos]].suf_len <= e->Tmax && ci + 1 <= max_items) {
+        cs += items[up.items[pos]].suf_len;
+        ++ci; ++pos;
+      }
+      bu.item_end = static_cast<int>(pos);
+      cur.push_back(bu);
+    }
+  }
+  flush();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ TVG pooled visual rows
+static int ensure_tvg_vis(blim_engine* e, cudaStream_t st) {
+  if (e->tvg_vis_ready) return 0;
+  if (e->n_videos <= 0) return e->fail("videos not set");
+  const int n_rows = e->n_videos * e->n_clips;  // pooled rows
+  CKE(e->tvg_vis.reserve(static_cast<size_t>(n_rows) * e->H * 2));
+  // chunk over whole clips so every chunk fits the visual staging buffer
+  const int clips_per_chunk = std::max(1, std::min(e->Pmax, e->Tmax) / e->TPC);
+  for (int c0 = 0; c0 < n_rows; c0 += clips_per_chunk) {
+    const int nc = std::min(clips_per_chunk, n_rows - c0);
+    CKR(project(e, e->feats.as<bf16>() + static_cast<size_t>(c0) * e->TPC * e->MM, nc * e->TPC, 1, e->vis.as<bf16>(), st));
+    mean_rows_kernel<<<nc, 256, 0, st>>>(e->tvg_vis.as<bf16>() + static_cast<size_t>(c0) * e->H, e->vis.as<bf16>(), nc, e->TPC, e->H);
+    CKL();
+  }
+  e->tvg_vis_ready = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ scoring: VTG / VTG prior
+static int score_vtg(blim_engine* e, bool prior, const std::vector<std::pair<int, int>>& keys /* (v, t) unique */, float* out_unique,
+                     cudaStream_t st) {
+  const TextTable& tt = e->texts[BLIM_TEXTS_VTG];
+  const int n_vis = e->n_clips * e->TPC;
+  // units: (video, prompt group) for the likelihood, (prompt group) for the prior
+  std::map<std::pair<int, int>, int> unit_of;
+  std::vector<UnitPlan> units;
+  std::vector<std::pair<int, int>> unit_key;
+  std::vector<Item> items(keys.size());
+  for (size_t i = 0; i < keys.size(); ++i) {
+    const int v = keys[i].first, t = keys[i].second;
+    const int g = tt.group[t];
+    const std::pair<int, int> uk(prior ? -1 : v, g);
+    auto it = unit_of.find(uk);
+    if (it == unit_of.end()) {
+      UnitPlan up;
+      up.prefix_len = static_cast<int>(tt.groups[g].pre.size() + tt.groups[g].post.size()) + (prior ? 0 : n_vis);
+      if (up.prefix_len == 0) return e->fail("empty VTG prompt");
+      units.push_back(up);
+      unit_key.push_back(uk);
+      it = unit_of.emplace(uk, static_cast<int>(units.size()) - 1).first;
+    }
+    const int n_tok = static_cast<int>(tt.off[t + 1] - tt.off[t]);
+    items[i].unit = it->second;
+    items[i].suf_len = n_tok - tt.first_lab[t] - 1;  // caption tokens except the last one (its state predicts nothing)
+    items[i].key = static_cast<int>(i);
+    units[it->second].items.push_back(static_cast<int>(i));
+  }
+  std::vector<std::vector<BatchUnit>> batches;
+  CKR(plan_batches(e, units, items, e->Tmax / 2, batches));
+
+  Run run;
+  for (const auto& batch : batches) {
+    // ---- projector for the distinct videos of the batch
+    std::map<int, int> vis_row0;  // video -> first row in e->vis
+    if (!prior) {
+      int rows = 0;
+      for (const BatchUnit& bu : batch) {
+        const int v = unit_key[bu.unit].first;
+        if (!vis_row0.count(v)) { vis_row0[v] = rows; rows += n_vis; }
+      }
+      // videos are contiguous in e->feats only per video: project video by video groups of consecutive ids
+      for (auto it = vis_row0.begin(); it != vis_row0.end();) {
+        // merge consecutive video ids that also got consecutive row ranges
+        auto jt = it;
+        int cnt = 1;
+        auto nx = std::next(jt);
+        while (nx != vis_row0.end() && nx->first == jt->first + 1 && nx->second == jt->second + n_vis) { jt = nx; nx = std::next(jt); ++cnt; }
+        CKR(project(e, e->feats.as<bf16>() + static_cast<size_t>(it->first) * n_vis * e->MM, cnt * n_vis, 0,
+                    e->vis.as<bf16>() + static_cast<size_t>(it->second) * e->H, st));
+        it = nx;
+      }
+    }
+    // ---- prefix run
+    run.clear();
+    std::vector<int> unit_start(batch.size()), unit_len(batch.size()), last_tok(batch.size());
+    for (size_t b = 0; b < batch.size(); ++b) {
+      const PromptGroup& g = tt.groups[unit_key[batch[b].unit].second];
+      unit_start[b] = run.begin_seq(0, 0);
+      int pos = 0;
+      for (int32_t id : g.pre) run.push(id, pos++);
+      if (!prior) {
+        const int r0 = vis_row0[unit_key[batch[b].unit].first];
+        for (int j = 0; j < n_vis; ++j) run.push(-1 - (r0 + j), pos++);
+      } else {
+        pos += n_vis;  // CPN: visual rows are invisible as keys but keep their rotary positions (modeling_videochat_flash.py:433)
+      }
+      for (int32_t id : g.post) run.push(id, pos++);
+      run.end_seq();
+      unit_len[b] = run.T() - unit_start[b];
+      last_tok[b] = run.T() - 1;
+    }
+    CKR(run_decoder(e, run, true, false, st));
+    CKR(save_prefix_last(e, last_tok, st));
+    // ---- suffix run
+    run.clear();
+    std::vector<int> row_idx, targets, row_off, item_keys;
+    row_off.push_back(0);
+    for (size_t b = 0; b < batch.size(); ++b) {
+      const UnitPlan& up = units[batch[b].unit];
+      const PromptGroup& g = tt.groups[unit_key[batch[b].unit].second];
+      const int pos0 = static_cast<int>(g.pre.size() + g.post.size()) + n_vis;
+      for (int ii = batch[b].item_begin; ii < batch[b].item_end; ++ii) {
+        const Item& it = items[up.items[ii]];
+        const int t = keys[it.key].second;
+        const int64_t base = tt.off[t];
+        const int fl = tt.first_lab[t];
+        const int q0 = run.begin_seq(unit_start[b], unit_len[b]);
+        for (int j = 0; j < it.suf_len; ++j) run.push(tt.ids[base + fl + j], pos0 + j);
+        run.end_seq();
+        // LM rows: last prefix state predicts the first label, suffix token j predicts label fl + 1 + j
+        row_idx.push_back(-1 - static_cast<int>(b));
+        targets.push_back(tt.labels[base + fl]);
+        for (int j = 0; j < it.suf_len; ++j) {
+          row_idx.push_back(q0 + j);
+          targets.push_back(tt.labels[base + fl + 1 + j]);
+        }
+        row_off.push_back(static_cast<int>(row_idx.size()));
+        item_keys.push_back(it.key);
+      }
+    }
+    CKR(run_decoder(e, run, false, false, st));
+    // ---- fused LM head over whole items, chunks of <= Tmax rows
+    const int n_items = static_cast<int>(item_keys.size());
+    int i0 = 0;
+    while (i0 < n_items) {
+      int i1 = i0;
+      while (i1 < n_items && row_off[i1 + 1] - row_off[i0] <= e->Tmax) ++i1;
+      if (i1 == i0) return e->fail("a caption has more scored tokens than max_run_tokens");
+      const int r0 = row_off[i0], R = row_off[i1] - r0;
+      CKR(upload(e, e->d_idx, row_idx.data() + r0, R * sizeof(int), st));
+      CKR(upload(e, e->d_targets, targets.data() + r0, R * sizeof(int), st));
+      std::vector<int> off_local(i1 - i0 + 1);
+      for (int i = i0; i <= i1; ++i) off_local[i - i0] = row_off[i] - r0;
+      CKR(upload(e, e->d_row_off, off_local.data(), off_local.size() * sizeof(int), st));
+      CKR(rmsnorm(e, e->lm_a.as<bf16>(), e->x.as<float>(), e->prefix_last.as<float>(), e->d_idx.as<int>(), e->norm.as<float>(), R, st));
+      CKR(lse_rows(e, e->lm_a.as<bf16>(), e->H, e->lm_head.as<bf16>(), e->H, R, e->V, e->H, e->d_targets.as<int>(), 1.0f, e->logp.as<float>(), st));
+      // item scores land in a staging area (reuse tgt_logit after finalize is done with it: stream ordered)
+      const int P = i1 - i0;
+      vtg_seq_mean_kernel<<<(P + 7) / 8, 256, 0, st>>>(e->tgt_logit.as<float>(), e->logp.as<float>(), e->d_row_off.as<int>(), P);
+      CKL();
+      // scatter to the unique-key slots
+      CKR(upload(e, e->d_idx, item_keys.data() + i0, P * sizeof(int), st));
+      {
+        // out_unique[key[i]] = staged[i]  (a scatter with n_cols = 1 row = key)
+        std::vector<int> zeros(P, 0);
+        CKR(upload(e, e->d_targets, zeros.data(), P * sizeof(int), st));
+        scatter_scores_kernel<<<(P + 255) / 256, 256, 0, st>>>(out_unique, 1, e->d_idx.as<int>(), e->d_targets.as<int>(), e->tgt_logit.as<float>(), P);
+        CKL();
+      }
+      i0 = i1;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ scoring: TVG / TVG prior
+// keys: likelihood -> (v, t); prior -> (v, t_representative) with one key per distinct (prefix group, T0, v).
+static int score_tvg(blim_engine* e, bool prior, const std::vector<std::pair<int, int>>& keys, float* out_unique, cudaStream_t st) {
+  const TextTable& tt = e->texts[BLIM_TEXTS_TVG];
+  if (!e->visual_head.p) return e->fail("visual_head weight not loaded");
+  if (!e->vocab.p) return e->fail("video vocab not set");
+  CKR(ensure_tvg_vis(e, st));
+  const int NC = e->n_clips;
+  // units: likelihood -> one per text (prefix = its T0 text tokens); prior -> one per distinct visible header
+  std::map<std::vector<int32_t>, int> hdr_units;
+  std::map<int, int> text_units;
+  std::vector<UnitPlan> units;
+  std::vector<int> unit_text;  // a text whose ids define the unit's prefix
+  std::vector<int> unit_plen;
+  std::vector<Item> items(keys.size());
+  for (size_t i = 0; i < keys.size(); ++i) {
+    const int t = keys[i].second;
+    const int T0 = tt.img_pos[t];
+    int u;
+    if (!prior) {
+      auto it = text_units.find(t);
+      if (it == text_units.end()) {
+        UnitPlan up; up.prefix_len = T0;
+        units.push_back(up); unit_text.push_back(t); unit_plen.push_back(T0);
+        it = text_units.emplace(t, static_cast<int>(units.size()) - 1).first;
+      }
+      u = it->second;
+      items[i].suf_len = NC - 1;
+    } else {
+      const int plen = std::min(e->tvg_prefix_len, T0 - 1);  // visible header; the last text token is handled in the suffix
+      std::vector<int32_t> hk(tt.ids.begin() + tt.off[t], tt.ids.begin() + tt.off[t] + plen);
+      auto it = hdr_units.find(hk);
+      if (it == hdr_units.end()) {
+        UnitPlan up; up.prefix_len = plen;
+        units.push_back(up); unit_text.push_back(t); unit_plen.push_back(plen);
+        it = hdr_units.emplace(hk, static_cast<int>(units.size()) - 1).first;
+      }
+      u = it->second;
+      items[i].suf_len = NC;  // [last text token] + NC-1 pooled visual rows
+    }
+    items[i].unit = u;
+    items[i].key = static_cast<int>(i);
+    units[u].items.push_back(static_cast<int>(i));
+  }
+  std::vector<std::vector<BatchUnit>> batches;
+  CKR(plan_batches(e, units, items, e->Tmax / std::max(1, NC), batches));
+
+  Run run;
+  const float scale = 1.0f / sqrtf(static_cast<float>(e->MM));
+  for (const auto& batch : batches) {
+    // ---- prefix run (text tokens only, embeddings)
+    run.clear();
+    std::vector<int> unit_start(batch.size()), unit_len(batch.size()), last_tok(batch.size());
+    bool any_prefix = false;
+    for (size_t b = 0; b < batch.size(); ++b) {
+      const int t = unit_text[batch[b].unit];
+      const int plen = unit_plen[batch[b].unit];
+      unit_start[b] = run.begin_seq(0, 0);
+      for (int j = 0; j < plen; ++j) run.push(tt.ids[tt.off[t] + j], j);
+      run.end_seq();
+      unit_len[b] = plen;
+      last_tok[b] = run.T() - 1;
+      any_prefix = any_prefix || plen > 0;
+    }
+    if (any_prefix) {
+      CKR(run_decoder(e, run, true, false, st));
+      if (!prior) CKR(save_prefix_last(e, last_tok, st));
+    }
+    // ---- suffix run.  Visual rows come straight from the pooled tvg_mlp table: tok_src = -1 - row, with e->vis
+    //      temporarily replaced by the table (assemble reads `visual` rows by index).
+    run.clear();
+    std::vector<int> item_keys, item_q0, item_unit_b;
+    for (size_t b = 0; b < batch.size(); ++b) {
+      const UnitPlan& up = units[batch[b].unit];
+      for (int ii = batch[b].item_begin; ii < batch[b].item_end; ++ii) {
+        const Item& it = items[up.items[ii]];
+        const int v = keys[it.key].first, t = keys[it.key].second;
+        const int T0 = tt.img_pos[t];
+        const int q0 = run.begin_seq(unit_start[b], unit_len[b]);
+        if (prior) {
+          // last text token: a query at position T0-1; as a key it is CPN-masked unless it lies inside the visible header
+          run.push(tt.ids[tt.off[t] + T0 - 1], T0 - 1, (T0 - 1) < e->tvg_prefix_len);
+        }
+        for (int c = 0; c < NC - 1; ++c) run.push(-1 - (v * NC + c), T0 + c);
+        run.end_seq();
+        item_keys.push_back(it.key);
+        item_q0.push_back(q0);
+        item_unit_b.push_back(static_cast<int>(b));
+      }
+    }
+    if (run.T() > 0) {
+      // assemble with the pooled table as the visual source
+      const int T = run.T();
+      CKR(upload(e, e->d_tok_src, run.tok_src.data(), T * sizeof(int), st));
+      assemble_tokens_kernel<<<T, 128, 0, st>>>(e->x.as<float>(), e->embed.as<bf16>(), e->tvg_vis.as<bf16>(), e->d_tok_src.as<int>(), T, e->H);
+      CKL();
+      CKR(run_decoder(e, run, false, true, st));
+    }
+    // ---- TVG head, chunks of items with NC * P <= Tmax rows, rows laid out clip-major [c][p]
+    const int n_items = static_cast<int>(item_keys.size());
+    const int max_p = std::max(1, e->Tmax / NC);
+    for (int i0 = 0; i0 < n_items; i0 += max_p) {
+      const int P = std::min(max_p, n_items - i0);
+      std::vector<int> row_idx(static_cast<size_t>(NC) * P), targets(P);
+      for (int p = 0; p < P; ++p) {
+        const int i = i0 + p;
+        for (int c = 0; c < NC; ++c) {
+          int src;
+          if (!prior) src = (c == 0) ? -1 - item_unit_b[i] : item_q0[i] + (c - 1);
+          else src = item_q0[i] + c;
+          row_idx[static_cast<size_t>(c) * P + p] = src;
+        }
+        targets[p] = e->video_labels[keys[item_keys[i]].first];
+      }
+      const int R = NC * P;
+      CKR(upload(e, e->d_idx, row_idx.data(), R * sizeof(int), st));
+      CKR(upload(e, e->d_targets, targets.data(), P * sizeof(int), st));
+      CKR(rmsnorm(e, e->lm_a.as<bf16>(), e->x.as<float>(), e->prefix_last.as<float>(), e->d_idx.as<int>(), e->norm.as<float>(), R, st));
+      EpiStore<bf16, false, false>::Params pv{e->pred.as<bf16>(), e->MM, nullptr};
+      CKR((gemm<EpiStore<bf16, false, false>>(e, e->lm_a.as<bf16>(), e->H, e->visual_head.as<bf16>(), e->H, R, e->MM, e->H, pv, st)));
+      for (int c = 0; c < NC; ++c) {
+        CKR(lse_rows(e, e->pred.as<bf16>() + static_cast<size_t>(c) * P * e->MM, e->MM, e->vocab.as<bf16>() + static_cast<size_t>(c) * e->n_vocab * e->MM,
+                     e->MM, P, e->n_vocab, e->MM, e->d_targets.as<int>(), scale, e->logp.as<float>() + static_cast<size_t>(c) * P, st));
+      }
+      tvg_clip_mean_kernel<<<(P + 255) / 256, 256, 0, st>>>(e->tgt_logit.as<float>(), e->logp.as<float>(), P, NC);
+      CKL();
+      CKR(upload(e, e->d_idx, item_keys.data() + i0, P * sizeof(int), st));
+      std::vector<int> zeros(P, 0);
+      CKR(upload(e, e->d_row_off, zeros.data(), P * sizeof(int), st));
+      scatter_scores_kernel<<<(P + 255) / 256, 256, 0, st>>>(out_unique, 1, e->d_idx.as<int>(), e->d_row_off.as<int>(), e->tgt_logit.as<float>(), P);
+      CKL();
+    }
+  }
+  return 0;
+}
+
+extern "C" int blim_score_pairs(blim_engine* e, int kind, const int32_t* pair_v, const int32_t* pair_t, int64_t n_pairs, float* out_dev,
+                                void* stream) {
+  if (!e) return 1;
+  if (n_pairs == 0) return 0;
+  if (!pair_v || !pair_t || !out_dev || n_pairs < 0 || n_pairs > (1ll << 30)) return e->fail("bad pair arguments");
+  if (kind < 0 || kind > 3) return e->fail("bad score kind");
+  CKE(cudaSetDevice(e->device));
+  CKR(check_ready(e));
+  cudaStream_t st = S(stream);
+  const bool is_tvg = kind == BLIM_TVG || kind == BLIM_TVG_PRIOR;
+  const bool prior = kind == BLIM_VTG_PRIOR || kind == BLIM_TVG_PRIOR;
+  const TextTable& tt = e->texts[is_tvg ? BLIM_TEXTS_TVG : BLIM_TEXTS_VTG];
+  if (tt.n == 0) return e->fail(is_tvg ? "TVG texts not set" : "VTG texts not set");
+  if (e->n_videos == 0) return e->fail("videos not set");
+  if (!is_tvg && !prior && (!e->proj[0].w0.p)) return e->fail("mm_projector.mlp weights not loaded");
+  // ---- unique keys
+  //   VTG: (v,t)   VTG prior: (t) [all videos share n_clips]   TVG: (v,t)   TVG prior: (header group, T0, v)
+  std::map<std::vector<int64_t>, int> key_of;
+  std::vector<std::pair<int, int>> keys;
+  std::vector<int> map(n_pairs);
+  auto make_key = [&](int v, int t) {
+    std::vector<int64_t> k;
+    if (kind == BLIM_VTG || kind == BLIM_TVG) k = {v, t};
+    else if (kind == BLIM_VTG_PRIOR) k = {t};
+    else {
+      // texts with the same visible header, the same length T0 and the same last text token give the same prior
+      const int T0 = tt.img_pos[t];
+      const int plen = std::min(e->tvg_prefix_len, T0 - 1);
+      k = {v, T0, tt.ids[tt.off[t] + T0 - 1]};
+      for (int j = 0; j < plen; ++j) k.push_back(tt.ids[tt.off[t] + j]);
+    }
+    return k;
+  };
+  for (int64_t i = 0; i < n_pairs; ++i) {
+    const int v = pair_v[i], t = pair_t[i];
+    if (v < 0 || v >= e->n_videos || t < 0 || t >= tt.n) return e->fail("pair index out of range");
+    key_of.emplace(make_key(v, t), static_cast<int>(i));  // remembers the first pair carrying this key
+  }
+  {
+    // key indices in sorted key order: VTG work is grouped by video, TVG work by (video, text)
+    int idx = 0;
+    keys.reserve(key_of.size());
+    for (auto& kv : key_of) {
+      const int first = kv.second;
+      keys.emplace_back(pair_v[first], pair_t[first]);
+      kv.second = idx++;
+    }
+  }
+  for (int64_t i = 0; i < n_pairs; ++i) map[i] = key_of.find(make_key(pair_v[i], pair_t[i]))->second;
+  CKE(e->uniq_scores.reserve(keys.size() * 4));
+  if (is_tvg) CKR(score_tvg(e, prior, keys, e->uniq_scores.as<float>(), st));
+  else CKR(score_vtg(e, prior, keys, e->uniq_scores.as<float>(), st));
+  CKR(upload(e, e->d_map, map.data(), map.size() * sizeof(int), st));
+  const int n = static_cast<int>(n_pairs);
+  expand_scores_kernel<<<(n + 255) / 256, 256, 0, st>>>(out_dev, e->uniq_scores.as<float>(), e->d_map.as<int>(), n);
+  CKL();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ compat forward
+extern "C" int blim_forward_logits(blim_engine* e, const void* embeds, const int32_t* mask_dev, int B, int L, float* logits, void* hidden,
+                                   void* stream) {
+  if (!e) return 1;
+  if (!embeds || B <= 0 || L <= 0) return e->fail("bad forward arguments");
+  CKE(cudaSetDevice(e->device));
+  CKR(check_ready(e));
+  cudaStream_t st = S(stream);
+  if (L > e->Tmax) return e->fail("sequence longer than max_run_tokens");
+  const int seq_per_run = std::max(1, e->Tmax / L);
+  std::vector<int32_t> mask_h;
+  if (mask_dev) {
+    mask_h.resize(static_cast<size_t>(B) * L);
+    CKE(cudaMemcpyAsync(mask_h.data(), mask_dev, mask_h.size() * 4, cudaMemcpyDeviceToHost, st));
+    CKE(cudaStreamSynchronize(st));
+  }
+  Run run;
+  for (int b0 = 0; b0 < B; b0 += seq_per_run) {
+    const int nb = std::min(seq_per_run, B - b0);
+    run.clear();
+    for (int b = 0; b < nb; ++b) {
+      run.begin_seq(0, 0);
+      for (int j = 0; j < L; ++j) run.push(0, j, mask_dev ? mask_h[static_cast<size_t>(b0 + b) * L + j] != 0 : true);
+      run.end_seq();
+    }
+    const int T = nb * L;
+    const size_t n = static_cast<size_t>(T) * e->H;
+    bf16_rows_to_f32_kernel<<<static_cast<unsigned>((n / 2 + 255) / 256), 256, 0, st>>>(
+        e->x.as<float>(), reinterpret_cast<const bf16*>(embeds) + static_cast<size_t>(b0) * L * e->H, n);
+    CKL();
+    CKR(run_decoder(e, run, false, true, st));
+    CKR(rmsnorm(e, e->lm_a.as<bf16>(), e->x.as<float>(), nullptr, nullptr, e->norm.as<float>(), T, st));
+    if (hidden)
+      CKE(cudaMemcpyAsync(reinterpret_cast<bf16*>(hidden) + static_cast<size_t>(b0) * L * e->H, e->lm_a.p, n * 2, cudaMemcpyDeviceToDevice, st));
+    if (logits) {
+      EpiStore<float, false, false>::Params p{logits + static_cast<size_t>(b0) * L * e->V, e->V, nullptr};
+      CKR((gemm<EpiStore<float, false, false>>(e, e->lm_a.as<bf16>(), e->H, e->lm_head.as<bf16>(), e->H, T, e->V, e->H, p, st)));
+    }
+  }
+  return 0;
+}
+
+extern "C" int blim_project_video(blim_engine* e, const void* feats, int n_rows, int tvg, void* out, void* stream) {
+  if (!e) return 1;
+  if (!feats || !out || n_rows < 0) return e->fail("bad projector arguments");
+  CKE(cudaSetDevice(e->device));
+  return project(e, reinterpret_cast<const bf16*>(feats), n_rows, tvg ? 1 : 0, reinterpret_cast<bf16*>(out), S(stream));
+}
+
+extern "C" int blim_forward_visual(blim_engine* e, const void* hidden, int n_rows, void* out, void* stream) {
+  if (!e) return 1;
+  if (!hidden || !out || n_rows < 0) return e->fail("bad forward_visual arguments");
+  if (!e->visual_head.p) return e->fail("visual_head weight not loaded");
+  CKE(cudaSetDevice(e->device));
+  EpiStore<bf16, false, false>::Params p{reinterpret_cast<bf16*>(out), e->MM, nullptr};
+  return gemm<EpiStore<bf16, false, false>>(e, reinterpret_cast<const bf16*>(hidden), e->H, e->visual_head.as<bf16>(), e->H, n_rows, e->MM, e->H, p,
+                                            S(stream));
+}
+
+__global__ void embed_rows_kernel(bf16* __restrict__ out, const bf16* __restrict__ embed, const int* __restrict__ ids, int n, int H) {
+  const int t = blockIdx.x;
+  if (t >= n) return;
+  const bf16* row = embed + static_cast<size_t>(ids[t]) * H;
+  for (int c = threadIdx.x * 8; c < H; c += blockDim.x * 8)
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * H + c) = *reinterpret_cast<const uint4*>(row + c);
+}
+extern "C" int blim_embed_tokens(blim_engine* e, const int32_t* ids_dev, int n, void* out, void* stream) {
+  if (!e) return 1;
+  if (!ids_dev || !out || n < 0) return e->fail("bad embed arguments");
+  if (!e->embed.p) return e->fail("embed_tokens weight not loaded");
+  if (n == 0) return 0;
+  CKE(cudaSetDevice(e->device));
+  embed_rows_kernel<<<n, 128, 0, S(stream)>>>(reinterpret_cast<bf16*>(out), e->embed.as<bf16>(), ids_dev, n, e->H);
+  CKL();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ fuse / rerank / scatter
+extern "C" int blim_fuse_rerank(blim_engine* e, const blim_fuse_cfg* c, const int32_t* cand_idx, const float* cand, const float* prior,
+                                const float* query, const float* iv2, int n_rows, int n_cols, int k, int row0, double* fused_out,
+                                int32_t* order_out, int32_t* gt_rank_out, int32_t* zero_count, void* stream) {
+  if (!e) return 1;
+  if (!c || !cand_idx || !iv2 || !fused_out || !order_out || !gt_rank_out || !zero_count || n_rows < 0 || n_cols <= 0 || k <= 0 || k > n_cols)
+    return e->fail("bad fuse_rerank arguments");
+  if (row0 < 0 || row0 + n_rows > n_cols) return e->fail("fuse_rerank: ground-truth column out of range (rows must be a slice of a square problem)");
+  if (n_rows == 0) return 0;
+  CKE(cudaSetDevice(e->device));
+  FuseCoef f;
+  f.alpha = static_cast<float>(c->alpha);
+  f.c_q = static_cast<float>(c->c_query);
+  f.c_q_om = static_cast<float>(1.0 - c->c_query);
+  f.c_e = static_cast<float>(c->c_ens);
+  f.c_e_om = static_cast<float>(1.0 - c->c_ens);
+  f.c_e_d = c->c_ens;
+  f.use_prior = c->use_prior && prior != nullptr;
+  f.use_query = c->use_query;
+  f.cpn_zero_f64 = c->cpn_zero_f64;
+  const size_t smem = static_cast<size_t>(k) * (sizeof(double) + sizeof(int)) + n_cols;
+  if (smem > 200 * 1024) return e->fail("fuse_rerank: row too wide for shared memory");
+  static bool attr = false;
+  if (!attr) {
+    CKE(cudaFuncSetAttribute(fuse_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  fuse_rerank_kernel<<<n_rows, 256, smem, S(stream)>>>(f, cand_idx, cand, prior, query, iv2, n_rows, n_cols, k, row0, fused_out, order_out,
+                                                        gt_rank_out, zero_count);
+  CKL();
+  return 0;
+}
+
+extern "C" int blim_rank_dense(blim_engine* e, const float* mat, int n_rows, int n_cols, int row0, int32_t* gt_rank_out, int32_t* zero_count,
+                               void* stream) {
+  if (!e) return 1;
+  if (!mat || !gt_rank_out || !zero_count || n_rows < 0 || n_cols <= 0 || row0 < 0 || row0 + n_rows > n_cols) return e->fail("bad rank_dense arguments");
+  if (n_rows == 0) return 0;
+  CKE(cudaSetDevice(e->device));
+  rank_dense_kernel<<<n_rows, 256, 0, S(stream)>>>(mat, n_rows, n_cols, row0, gt_rank_out, zero_count);
+  CKL();
+  return 0;
+}
+
+extern "C" int blim_scatter_scores(blim_engine* e, float* dense, int n_rows, int n_cols, int do_fill, float fill, const int32_t* row,
+                                   const int32_t* col, const float* val, int64_t n, void* stream) {
+  if (!e) return 1;
+  if (!dense || n_rows <= 0 || n_cols <= 0 || n < 0 || (n > 0 && (!row || !col || !val))) return e->fail("bad scatter arguments");
+  CKE(cudaSetDevice(e->device));
+  if (do_fill) {
+    const size_t tot = static_cast<size_t>(n_rows) * n_cols;
+    fill_f32_kernel<<<static_cast<unsigned>(std::min<size_t>((tot + 255) / 256, 4096)), 256, 0, S(stream)>>>(dense, fill, tot);
+    CKL();
+  }
+  if (n > 0) {
+    scatter_scores_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, S(stream)>>>(dense, n_cols, row, col, val, static_cast<int>(n));
+    CKL();
+  }
+  return 0;
+}
+
+extern "C" int64_t blim_kernel_launches(const blim_engine* e) { return e ? e->launches + e->gemm.launches : 0; }
+extern "C" double blim_gemm_flops(const blim_engine* e) { return e ? e->flops : 0.0; }
+
+// ------------------------------------------------------------------------------------------------ debug GEMM entry
+extern "C" int blim_debug_gemm(blim_engine* e, int epilogue, const void* A, const void* W, void* C, int M, int N, int K, const float* bias,
+                               const int32_t* target, float scale, int cta_group, void* stream) {
+  if (!e) return 1;
+  if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0) return e->fail("bad debug_gemm arguments");
+  CKE(cudaSetDevice(e->device));
+  cudaStream_t st = S(stream);
+  const int saved = e->gemm.cta_group;
+  if (cta_group == 1 || cta_group == 2) e->gemm.cta_group = cta_group;
+  const bf16* a = reinterpret_cast<const bf16*>(A);
+  const bf16* w = reinterpret_cast<const bf16*>(W);
+  int r = 0;
+  switch (epilogue) {
+    case 0: { EpiStore<bf16, false, false>::Params p{reinterpret_cast<bf16*>(C), N, nullptr}; r = gemm<EpiStore<bf16, false, false>>(e, a, K, w, K, M, N, K, p, st); break; }
+    case 1: { EpiStore<bf16, true, false>::Params p{reinterpret_cast<bf16*>(C), N, bias}; r = gemm<EpiStore<bf16, true, false>>(e, a, K, w, K, M, N, K, p, st); break; }
+    case 2: { EpiStore<bf16, true, true>::Params p{reinterpret_cast<bf16*>(C), N, bias}; r = gemm<EpiStore<bf16, true, true>>(e, a, K, w, K, M, N, K, p, st); break; }
+    case 3: { EpiStore<float, false, false>::Params p{reinterpret_cast<float*>(C), N, nullptr}; r = gemm<EpiStore<float, false, false>>(e, a, K, w, K, M, N, K, p, st); break; }
+    case 4: { EpiResid::Params p{reinterpret_cast<float*>(C), N}; r = gemm<EpiResid>(e, a, K, w, K, M, N, K, p, st); break; }
+    case 5: { EpiSwiglu::Params p{reinterpret_cast<bf16*>(C), N / 2}; r = gemm<EpiSwiglu>(e, a, K, w, K, M, N, K, p, st); break; }
+    case 6: {
+      if (M > e->Tmax) { r = e->fail("debug_gemm lse: M exceeds max_run_tokens"); break; }
+      r = lse_rows(e, a, K, w, K, M, N, K, target, scale, reinterpret_cast<float*>(C), st);
+      break;
+    }
+    default: r = e->fail("unknown epilogue");
+  }
+  e->gemm.cta_group = saved;
+  return r;
+}

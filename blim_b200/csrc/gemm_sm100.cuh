@@ -1,0 +1,539 @@
+// tcgen05 / TMEM / TMA GEMM core for sm_100a:  C[M,N] = A[M,K] · W[N,K]^T  (both operands K-major bf16, fp32 accumulate in TMEM)
+// with pluggable epilogues.  This one mainloop serves every dense contraction of the BLiM scoring path:
+//   projector MLPs            (reference: videochat_flash/mm_projector_builder.py:156-159)  -> EpiStore (bias, bias+GELU)
+//   fused QKV + bias + RoPE   (reference: modeling_qwen2_flash.py:666-679, 147-172)         -> EpiQkvRope
+//   o_proj / down_proj + res. (reference: modeling_qwen2_flash.py:714, 784, 790)            -> EpiResid
+//   gate|up + SwiGLU          (reference: modeling_qwen2_flash.py:188)                      -> EpiSwiglu
+//   LM head + log-softmax     (reference: modeling_qwen2_flash.py:1452-1453 + retrieval_utils.py:23-33) -> EpiLse
+//   TVG head                  (reference: retrieval_utils.py:104-107)                       -> EpiStore + EpiLse
+//
+// Kernel anatomy (one persistent CTA, or CTA pair, per SM):
+//   warp 0   TMA producer      : cp.async.bulk.tensor (SWIZZLE_128B) -> kStages-deep smem ring, mbarrier full/empty
+//   warp 1   MMA issuer        : one elected thread issues tcgen05.mma (M=128·cta_group, N=256, K=16), tcgen05.commit frees slots
+//   warp 2   TMEM allocator    : 512 columns = 2 accumulator stages of 256 fp32 columns
+//   warps 4-7 epilogue         : tcgen05.ld (one TMEM lane = one output row per thread) -> fused epilogue -> global
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "ptx_sm100.cuh"
+
+namespace blim {
+
+constexpr int kBM = 128;   // rows per CTA
+constexpr int kBN = 256;   // columns per tile (= one UMMA N)
+constexpr int kBK = 64;    // K per pipeline stage: 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kTmemCols = 512;
+
+template <int kCtaGroup>
+struct GemmCfg {
+  static constexpr int kStages = kCtaGroup == 1 ? 4 : 6;
+  static constexpr int kBRows = kBN / kCtaGroup;  // B rows staged by each CTA
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = kBRows * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+};
+
+struct GemmDims {
+  int M, N, K;
+  int m_tiles;   // number of (kBM*cta_group)-row tiles
+  int n_tiles;   // number of kBN-column tiles
+  int sb_tiles;  // m-tiles per super-block (L2 blocking of the A operand)
+};
+
+// tile t -> (m_tile, n_tile): super-blocks of sb_tiles m-tiles; inside a super-block m runs fastest so the CTAs that run
+// concurrently share a handful of W tiles while the A super-block stays L2-resident.
+__device__ __forceinline__ void tile_coords(const GemmDims& d, int t, int& m_tile, int& n_tile) {
+  const int per_sb = d.sb_tiles * d.n_tiles;
+  const int sb = t / per_sb;
+  const int base_m = sb * d.sb_tiles;
+  const int msz = min(d.sb_tiles, d.m_tiles - base_m);
+  const int r = t - sb * per_sb;
+  n_tile = r / msz;
+  m_tile = base_m + (r - n_tile * msz);
+}
+
+// ------------------------------------------------------------------------------------------------ epilogue helpers
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Store 32 consecutive bf16 of one row (this thread's row).  `valid` = number of in-range columns (<= 32).
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float (&v)[32], int valid) {
+  if (valid >= 32) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u;
+      u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+      u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+      u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+      u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      d4[i] = u;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < valid) dst[i] = __float2bfloat16(v[i]);
+  }
+}
+__device__ __forceinline__ void store_row32_f32(float* dst, const float (&v)[32], int valid) {
+  if (valid >= 32) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < valid) dst[i] = v[i];
+  }
+}
+__device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// Every epilogue gets: this thread's global row (may be >= M: loads from TMEM still have to be executed warp-uniformly,
+// only the global-memory side is predicated), the tile's first column n0, and the TMEM address of (its lane, column 0
+// of the accumulator stage).
+
+// out[row, col] = act(acc + bias[col])   OutT = __nv_bfloat16 or float
+template <typename OutT, bool kBias, bool kGelu>
+struct EpiStore {
+  struct Params {
+    OutT* out;
+    int ldo;
+    const float* bias;
+  };
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr) {
+    const bool row_ok = row < d.M;
+#pragma unroll 1
+    for (int c = 0; c < kBN; c += 32) {
+      float v[32];
+      tmem_ld32f(taddr + c, v);
+      const int col = n0 + c;
+      const int valid = d.N - col;
+      if (valid <= 0) continue;  // warp-uniform
+      if constexpr (kBias) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < valid) v[i] += __ldg(p.bias + col + i);
+      }
+      if constexpr (kGelu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      }
+      if (row_ok) {
+        OutT* dst = p.out + static_cast<size_t>(row) * p.ldo + col;
+        if constexpr (sizeof(OutT) == 2)
+          store_row32_bf16(reinterpret_cast<__nv_bfloat16*>(dst), v, valid);
+        else
+          store_row32_f32(reinterpret_cast<float*>(dst), v, valid);
+      }
+    }
+  }
+};
+
+// resid[row, col] += acc     (fp32 residual stream, in place)
+struct EpiResid {
+  struct Params {
+    float* resid;
+    int ldo;
+  };
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr) {
+    const bool row_ok = row < d.M;
+#pragma unroll 1
+    for (int c = 0; c < kBN; c += 32) {
+      float v[32];
+      tmem_ld32f(taddr + c, v);
+      const int col = n0 + c;
+      const int valid = d.N - col;
+      if (valid <= 0) continue;
+      if (row_ok) {
+        float* dst = p.resid + static_cast<size_t>(row) * p.ldo + col;
+        if (valid >= 32) {
+          float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 r = d4[i];
+            r.x += v[4 * i]; r.y += v[4 * i + 1]; r.z += v[4 * i + 2]; r.w += v[4 * i + 3];
+            d4[i] = r;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < valid) dst[i] += v[i];
+        }
+      }
+    }
+  }
+};
+
+// Fused QKV projection epilogue: + bias, rotary embedding on Q and K heads (half-split rotation, per-token position
+// looked up in a host-built cos/sin table), Q -> q_out[token], K/V -> kv cache rows kv_slot[token].
+// Column layout of the fused weight: [ Q heads | K heads | V heads ], every head head_dim wide; kBN is a multiple of head_dim.
+template <int kHeadDim>
+struct EpiQkvRope {
+  struct Params {
+    __nv_bfloat16* q_out;  // [M, n_q]
+    __nv_bfloat16* k_out;  // [slots, n_kv]
+    __nv_bfloat16* v_out;  // [slots, n_kv]
+    const float* bias;     // [n_q + 2 n_kv]
+    const int* pos;        // [M] rotary position of each token
+    const int* kv_slot;    // [M] cache row of each token (nullptr: row index)
+    const float* cos_tab;  // [max_pos, kHeadDim/2]
+    const float* sin_tab;
+    int n_q, n_kv;
+  };
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr) {
+    constexpr int kHalf = kHeadDim / 2;
+    const bool row_ok = row < d.M;
+    int pos = 0, slot = 0;
+    if (row_ok) {
+      pos = __ldg(p.pos + row);
+      slot = p.kv_slot ? __ldg(p.kv_slot + row) : row;
+    }
+    const float* cosr = p.cos_tab + static_cast<size_t>(pos) * kHalf;
+    const float* sinr = p.sin_tab + static_cast<size_t>(pos) * kHalf;
+#pragma unroll 1
+    for (int h = 0; h < kBN / kHeadDim; ++h) {
+      const int c0 = n0 + h * kHeadDim;  // first fused column of this head
+      if (c0 >= d.N) break;              // warp-uniform
+      __nv_bfloat16* dst;
+      bool rope;
+      if (c0 < p.n_q) {
+        dst = p.q_out + static_cast<size_t>(row) * p.n_q + c0;
+        rope = true;
+      } else if (c0 < p.n_q + p.n_kv) {
+        dst = p.k_out + static_cast<size_t>(slot) * p.n_kv + (c0 - p.n_q);
+        rope = true;
+      } else {
+        dst = p.v_out + static_cast<size_t>(slot) * p.n_kv + (c0 - p.n_q - p.n_kv);
+        rope = false;
+      }
+#pragma unroll 1
+      for (int j = 0; j < kHalf; j += 32) {
+        float lo[32], hi[32];
+        tmem_ld32f(taddr + h * kHeadDim + j, lo);
+        tmem_ld32f(taddr + h * kHeadDim + kHalf + j, hi);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          lo[i] += __ldg(p.bias + c0 + j + i);
+          hi[i] += __ldg(p.bias + c0 + kHalf + j + i);
+        }
+        if (rope && row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float cs = __ldg(cosr + j + i), sn = __ldg(sinr + j + i);
+            const float a = lo[i], b = hi[i];
+            lo[i] = a * cs - b * sn;  // q*cos + rotate_half(q)*sin, first half:  q1*cos - q2*sin
+            hi[i] = b * cs + a * sn;  //                              second half: q2*cos + q1*sin
+          }
+        }
+        if (row_ok) {
+          store_row32_bf16(dst + j, lo, 32);
+          store_row32_bf16(dst + kHalf + j, hi, 32);
+        }
+      }
+    }
+  }
+};
+
+// SwiGLU: the fused gate|up weight is interleaved in 128-row blocks, so tile n holds gate[128n..128n+127] in columns
+// 0..127 and up[128n..128n+127] in columns 128..255.  act[row, 128 n + c] = silu(gate) * up.
+struct EpiSwiglu {
+  struct Params {
+    __nv_bfloat16* act;  // [M, I]
+    int ldo;             // = I
+  };
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr) {
+    const bool row_ok = row < d.M;
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      float g[32], u[32];
+      tmem_ld32f(taddr + c, g);
+      tmem_ld32f(taddr + 128 + c, u);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float x = g[i];
+        g[i] = (x / (1.0f + __expf(-x))) * u[i];
+      }
+      if (row_ok) store_row32_bf16(p.act + static_cast<size_t>(row) * p.ldo + n_tile * 128 + c, g, 32);
+    }
+  }
+};
+
+// Fused "logits never materialised" epilogue: per row, the running (max, sum-exp) over this tile's columns of
+// scale*acc, plus the scaled logit of the row's target column if it falls into this tile.
+struct EpiLse {
+  struct Params {
+    float2* partial;    // [M, n_tiles] (max, sumexp)
+    float* tgt_logit;   // [M]
+    const int* target;  // [M]
+    float scale;
+  };
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr) {
+    const bool row_ok = row < d.M;
+    const int tgt = row_ok ? __ldg(p.target + row) : -1;
+    constexpr float kLog2e = 1.4426950408889634f;
+    float m_run = -INFINITY, s_run = 0.f, t_val = 0.f;
+    bool t_hit = false;
+#pragma unroll 1
+    for (int c = 0; c < kBN; c += 32) {
+      float v[32];
+      tmem_ld32f(taddr + c, v);
+      const int col = n0 + c;
+      const int valid = d.N - col;
+      if (valid <= 0) continue;
+      float cm = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = (i < valid) ? v[i] * p.scale : -INFINITY;
+        cm = fmaxf(cm, v[i]);
+      }
+      const int tc = tgt - col;
+      if (tc >= 0 && tc < 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i == tc) t_val = v[i];
+        t_hit = true;
+      }
+      const float m_new = fmaxf(m_run, cm);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s += exp2f((v[i] - m_new) * kLog2e);
+      s_run = s_run * exp2f((m_run - m_new) * kLog2e) + s;
+      m_run = m_new;
+    }
+    if (row_ok) {
+      p.partial[static_cast<size_t>(row) * d.n_tiles + n_tile] = make_float2(m_run, s_run);
+      if (t_hit) p.tgt_logit[row] = t_val;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <class Epi, int kCtaGroup>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDims dims,
+                    const typename Epi::Params ep) {
+  using Cfg = GemmCfg<kCtaGroup>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* s_a = smem;
+  uint8_t* s_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* bar_empty = bar_full + Cfg::kStages;
+  uint64_t* bar_tfull = bar_empty + Cfg::kStages;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int worker = blockIdx.x / kCtaGroup;       // persistent worker (CTA or CTA pair) index
+  const int n_workers = gridDim.x / kCtaGroup;
+  const int total_tiles = dims.m_tiles * dims.n_tiles;
+  const int num_kb = dims.K / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tempty[i], 128 * kCtaGroup);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kCtaGroup>(tmem_slot, kTmemCols);
+  tc_fence_before();
+  if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================== TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = worker; t < total_tiles; t += n_workers) {
+      int m_tile, n_tile;
+      tile_coords(dims, t, m_tile, n_tile);
+      const int m0 = m_tile * (kBM * kCtaGroup) + static_cast<int>(cta_rank) * kBM;
+      const int n0 = n_tile * kBN + static_cast<int>(cta_rank) * Cfg::kBRows;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&bar_empty[stage], phase ^ 1);
+        if (is_leader) mbar_arrive_expect_tx(&bar_full[stage], Cfg::kStageBytes * kCtaGroup);
+        if constexpr (kCtaGroup == 1) {
+          tma_load_2d(s_a + stage * Cfg::kABytes, &tm_a, &bar_full[stage], kb * kBK, m0);
+          tma_load_2d(s_b + stage * Cfg::kBBytes, &tm_b, &bar_full[stage], kb * kBK, n0);
+        } else {
+          tma_load_2d_pair(s_a + stage * Cfg::kABytes, &tm_a, &bar_full[stage], kb * kBK, m0);
+          tma_load_2d_pair(s_b + stage * Cfg::kBBytes, &tm_b, &bar_full[stage], kb * kBK, n0);
+        }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && is_leader) {
+    // ===================================================== MMA issuer (single thread)
+    constexpr uint32_t idesc = make_idesc_bf16(kBM * kCtaGroup, kBN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = worker; t < total_tiles; t += n_workers) {
+      mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kBN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&bar_full[stage], phase);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc_sw128(smem_u32(s_a + stage * Cfg::kABytes));
+        const uint64_t db = make_smem_desc_sw128(smem_u32(s_b + stage * Cfg::kBBytes));
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          // advance 16 elements = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+          umma_bf16<kCtaGroup>(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+        }
+        if constexpr (kCtaGroup == 1) umma_commit(&bar_empty[stage]); else umma_commit_pair(&bar_empty[stage]);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      if constexpr (kCtaGroup == 1) umma_commit(&bar_tfull[acc]); else umma_commit_pair(&bar_tfull[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (4 warps = 128 TMEM lanes = 128 rows)
+    const int ew = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = worker; t < total_tiles; t += n_workers) {
+      int m_tile, n_tile;
+      tile_coords(dims, t, m_tile, n_tile);
+      const int row = m_tile * (kBM * kCtaGroup) + static_cast<int>(cta_rank) * kBM + ew * 32 + lane;
+      mbar_wait(&bar_tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBN);
+      Epi::run(ep, dims, row, n_tile * kBN, n_tile, taddr);
+      tc_fence_before();
+      if (is_leader) mbar_arrive(&bar_tempty[acc]); else mbar_arrive_cluster(&bar_tempty[acc], 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // ===================================================== teardown
+  tc_fence_before();
+  if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<kCtaGroup>(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, cols] matrix, row pitch ld elements; box = 64 columns x box_rows rows, 128 B swizzle.
+inline bool make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+struct GemmLaunchCtx {
+  int num_sms = 148;
+  int cta_group = 1;  // 1: one CTA per tile, 2: CTA pairs (cta_group::2, 256-row tiles)
+  long long launches = 0;
+};
+
+template <class Epi, int kCtaGroup>
+inline cudaError_t launch_gemm_impl(GemmLaunchCtx& ctx, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N,
+                                    int K, const typename Epi::Params& ep, cudaStream_t stream) {
+  using Cfg = GemmCfg<kCtaGroup>;
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if (K <= 0 || (K % kBK) != 0) return cudaErrorInvalidValue;
+  CUtensorMap ta, tb;
+  if (!make_tmap_bf16(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), kBM)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw), Cfg::kBRows)) return cudaErrorInvalidValue;
+  GemmDims d;
+  d.M = M; d.N = N; d.K = K;
+  const int tile_m = kBM * kCtaGroup;
+  d.m_tiles = (M + tile_m - 1) / tile_m;
+  d.n_tiles = (N + kBN - 1) / kBN;
+  // keep the A super-block (sb_tiles * tile_m rows of K bf16) around 40 MB so it stays L2 resident
+  long long sb = (40ll << 20) / (static_cast<long long>(tile_m) * K * 2);
+  if (sb < 2) sb = 2;
+  if (sb > 64) sb = 64;
+  d.sb_tiles = static_cast<int>(sb);
+  const int total = d.m_tiles * d.n_tiles;
+  int workers = ctx.num_sms / kCtaGroup;
+  if (workers > total) workers = total;
+  auto kern = gemm_tcgen05_kernel<Epi, kCtaGroup>;
+  static bool attr_set = false;  // one static per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(workers * kCtaGroup));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtaGroup;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ctx.launches++;
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, d, ep);
+}
+
+template <class Epi>
+inline cudaError_t launch_gemm(GemmLaunchCtx& ctx, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+                               const typename Epi::Params& ep, cudaStream_t stream) {
+  if (ctx.cta_group == 2) return launch_gemm_impl<Epi, 2>(ctx, A, lda, W, ldw, M, N, K, ep, stream);
+  return launch_gemm_impl<Epi, 1>(ctx, A, lda, W, ldw, M, N, K, ep, stream);
+}
+
+}  // namespace blim

@@ -1,0 +1,107 @@
+"""TEST INFRASTRUCTURE -- imports the UNMODIFIED reference (mlvlab/BLiM) from /root/reference to pin the oracle.
+
+Only usable in the build container (the GPU box has no /root/reference); nothing in the product imports this.
+It is used by oracle/make_golden.py to generate the fixtures under tests/golden/ and by the (CPU) tests that compare
+oracle/blim_oracle.py with the real reference when the reference tree is present.
+
+Shims: stub modules for packages the vision tower / video IO import but the scoring path never
+calls (timm.layers, av, imageio, decord), and three transformers-5 workarounds on the config object.
+"""
+import os
+import sys
+import types
+
+import torch
+
+REF_ROOT = os.environ.get("BLIM_REF", "/root/reference")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REF_ROOT, "videochat_flash"))
+
+
+def _install_stubs():
+    import transformers  # noqa: F401  (must be imported before the stubs shadow anything it probes)
+
+    def stub(name, **attrs):
+        if name in sys.modules:
+            return sys.modules[name]
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    try:
+        import timm.layers  # noqa: F401
+    except Exception:
+        timm = stub("timm")
+        layers = stub("timm.layers", drop_path=lambda x, p=0.0, training=False: x, to_2tuple=lambda x: (x, x),
+                      trunc_normal_=lambda t, std=0.02: torch.nn.init.trunc_normal_(t, std=std))
+        timm.layers = layers
+    for name in ("av", "imageio"):
+        try:
+            __import__(name)
+        except Exception:
+            stub(name)
+    try:
+        import decord  # noqa: F401
+    except Exception:
+        stub("decord", VideoReader=object, cpu=lambda *a, **k: None)
+
+
+def import_reference():
+    """Returns (retrieval_utils, training_utils, modeling_videochat_flash) modules of the reference."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REF_ROOT}")
+    _install_stubs()
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    import retrieval_utils  # noqa: E402
+    import training_utils  # noqa: E402
+    from videochat_flash import modeling_videochat_flash as mvf  # noqa: E402
+    return retrieval_utils, training_utils, mvf
+
+
+class _Wrap(torch.nn.Module):
+    """evaluation()/compute_*_scores_x expect a DDP-like object with `.module` (retrieval_utils.py:66)."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *a, **k):
+        return self.module(*a, **k)
+
+
+def build_reference_model(cfg, state_dict, dtype=torch.float32, image_token_id=None):
+    """Instantiate the reference VideoChatFlashQwenForCausalLM for `cfg` (blim_b200.engine.ModelConfig) and load
+    `state_dict` (reference parameter names).  Returns the wrapped model (with .module) and the reference modules."""
+    ru, tu, mvf = import_reference()
+    c = mvf.VideoChatFlashQwenConfig(
+        hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_layers, num_attention_heads=cfg.num_heads,
+        num_key_value_heads=cfg.num_kv_heads, intermediate_size=cfg.intermediate_size, vocab_size=cfg.vocab_size,
+        rms_norm_eps=cfg.rms_norm_eps, max_position_embeddings=cfg.max_positions, hidden_act="silu",
+        use_sliding_window=False, attention_dropout=0.0, tie_word_embeddings=False)
+    c.mm_vision_tower = "umt-hd-stub"
+    c.delay_load = True
+    c.mm_projector_type = "tome16_mlp_hd64"
+    c.vision_encode_type = "video_image"
+    c.mm_patch_merge_type = "spatial_nopad"
+    c.mm_newline_position = "nothing"
+    c.mm_local_num_frames = 4
+    c.mm_vision_select_layer = -2
+    c.mm_hidden_size = cfg.mm_hidden_size
+    c.mm_pos_num_frames = 8
+    c.tokenizer_padding_side = "right"
+    c.use_cache = False
+    c._attn_implementation = "sdpa"
+    object.__setattr__(c, "rope_theta", cfg.rope_theta)
+    model = mvf.VideoChatFlashQwenForCausalLM(c)
+    missing, unexpected = model.load_state_dict(state_dict, strict=False)
+    need = [k for k in missing if not k.startswith("model.vision_tower") and "rotary_emb" not in k]
+    assert not need, f"reference parameters not provided: {need[:5]}"
+    model = model.to(dtype).eval()
+    if image_token_id is not None:
+        ru.IMAGE_TOKEN_ID = image_token_id  # small vocabularies: remap the module attribute (retrieval_utils.py:14,99)
+    return _Wrap(model), (ru, tu, mvf)
