@@ -57,6 +57,8 @@ SIGNATURES = {
     "blim_scatter_scores": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_f32, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "blim_kernel_launches": (c_i64, [c_void_p]),
     "blim_gemm_flops": (c_f64, [c_void_p]),
+    "blim_profile": (c_int, [c_void_p, c_int]),
+    "blim_profile_read": (c_int, [c_void_p, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "blim_debug_gemm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_f32, c_int, c_void_p]),
 }

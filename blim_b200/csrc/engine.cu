@@ -140,6 +140,26 @@ struct blim_engine {
   DevBuf d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map;
   size_t partial_tiles = 0;
 
+  // optional per-launch device timing (bench.py roofline): CUDA events around every GEMM / attention launch
+  bool profiling = false;
+  struct Timed { cudaEvent_t a, b; int cat; };
+  std::vector<Timed> timed;
+  std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t get_event() {
+    if (!event_pool.empty()) { cudaEvent_t ev = event_pool.back(); event_pool.pop_back(); return ev; }
+    cudaEvent_t ev; cudaEventCreate(&ev); return ev;
+  }
+  void tic(int cat, cudaStream_t st) {
+    if (!profiling) return;
+    Timed t; t.a = get_event(); t.b = get_event(); t.cat = cat;
+    cudaEventRecord(t.a, st);
+    timed.push_back(t);
+  }
+  void toc(cudaStream_t st) {
+    if (!profiling) return;
+    cudaEventRecord(timed.back().b, st);
+  }
+
   int fail(const std::string& m) {
     err = m;
     return 1;
@@ -174,7 +194,9 @@ template <class Epi>
 static int gemm(blim_engine* e, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const typename Epi::Params& p,
                 cudaStream_t st) {
   if (M <= 0) return 0;
+  e->tic(0, st);
   cudaError_t r = launch_gemm<Epi>(e->gemm, A, lda, W, ldw, M, N, K, p, st);
+  e->toc(st);
   if (r != cudaSuccess) return e->fail_cuda("tcgen05 gemm launch", r);
   e->flops += 2.0 * M * static_cast<double>(N) * K;
   return 0;
@@ -207,6 +229,8 @@ extern "C" void blim_destroy(blim_engine* e) {
     l.w_qkv.release(); l.w_o.release(); l.w_gu.release(); l.w_down.release(); l.b_qkv.release(); l.ln1.release(); l.ln2.release();
   }
   for (ProjW& p : e->proj) { p.w0.release(); p.b0.release(); p.w2.release(); p.b2.release(); }
+  for (auto& t : e->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -237,7 +261,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
   e->Pmax = cfg->max_prefix_tokens > 0 ? cfg->max_prefix_tokens : 32768;
   e->Umax = std::min(e->Pmax, 8192);
   e->gemm.num_sms = prop.multiProcessorCount;
-  e->gemm.cta_group = cfg->gemm_cta_group == 2 ? 2 : 1;
+  e->gemm.cta_group = cfg->gemm_cta_group == 1 ? 1 : 2;  // default: CTA pairs (cta_group::2)
   auto bad = [&](const char* m) {
     g_create_error = m;
     delete e;
@@ -538,10 +562,11 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
     ap.seqs = e->d_seqs.as<AttnSeq>(); ap.works = e->d_works.as<AttnWork>();
     ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G;
     ap.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(e->DH));
+    e->tic(1, st);
     cudaError_t r = launch_attention(ap, static_cast<int>(works.size()), e->NKV, e->DH, st);
+    e->toc(st);
     if (r != cudaSuccess) return e->fail_cuda("attention launch", r);
     e->launches++;
-    e->flops += 0.0;  // attention FLOPs are accounted analytically by bench.py
     EpiResid::Params pr{e->x.as<float>(), e->H};
     CKR(gemm<EpiResid>(e, e->attn.as<bf16>(), e->NQ, w.w_o.as<bf16>(), e->NQ, T, e->H, e->NQ, pr, st));
     CKR(rmsnorm(e, e->xn.as<bf16>(), e->x.as<float>(), nullptr, nullptr, w.ln2.as<float>(), T, st));
@@ -593,6 +618,7 @@ static int plan_batches(blim_engine* e, const std::vector<UnitPlan>& units, cons
                         std::vector<std::vector<BatchUnit>>& batches) {
   batches.clear();
   std::vector<BatchUnit> cur;
+  const int pcap = std::min(e->Pmax, e->Tmax);  // a prefix run is also one decoder run
   long long cp = 0, cs = 0;
   int ci = 0;
   auto flush = [&]() {
@@ -606,7 +632,7 @@ static int plan_batches(blim_engine* e, const std::vector<UnitPlan>& units, cons
     while (pos < up.items.size()) {
       const int first_len = items[up.items[pos]].suf_len;
       if (first_len > e->Tmax) return e->fail("a suffix sequence exceeds max_run_tokens");
-      if (cp + up.prefix_len > e->Pmax || static_cast<int>(cur.size()) + 1 > e->Umax || cs + first_len > e->Tmax || ci + 1 > max_items) flush();
+      if (cp + up.prefix_len > pcap || static_cast<int>(cur.size()) + 1 > e->Umax || cs + first_len > e->Tmax || ci + 1 > max_items) flush();
       BatchUnit bu{static_cast<int>(u), static_cast<int>(pos), static_cast<int>(pos)};
       cp += up.prefix_len;
       while (pos < up.items.size() && cs + items[up.items[pos]].suf_len <= e->Tmax && ci + 1 <= max_items) {
@@ -1106,6 +1132,32 @@ extern "C" int blim_scatter_scores(blim_engine* e, float* dense, int n_rows, int
     scatter_scores_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, S(stream)>>>(dense, n_cols, row, col, val, static_cast<int>(n));
     CKL();
   }
+  return 0;
+}
+
+extern "C" int blim_profile(blim_engine* e, int enable) {
+  if (!e) return 1;
+  e->profiling = enable != 0;
+  return 0;
+}
+// Synchronises the device, sums the recorded event intervals per category (0 = tcgen05 GEMM, 1 = attention) and resets.
+extern "C" int blim_profile_read(blim_engine* e, double* gemm_ms, double* attn_ms, int64_t* gemm_launches, int64_t* attn_launches) {
+  if (!e) return 1;
+  CKE(cudaSetDevice(e->device));
+  CKE(cudaDeviceSynchronize());
+  double ms[2] = {0.0, 0.0};
+  int64_t n[2] = {0, 0};
+  for (auto& t : e->timed) {
+    float f = 0.f;
+    if (cudaEventElapsedTime(&f, t.a, t.b) == cudaSuccess) { ms[t.cat] += f; n[t.cat]++; }
+    e->event_pool.push_back(t.a);
+    e->event_pool.push_back(t.b);
+  }
+  e->timed.clear();
+  if (gemm_ms) *gemm_ms = ms[0];
+  if (attn_ms) *attn_ms = ms[1];
+  if (gemm_launches) *gemm_launches = n[0];
+  if (attn_launches) *attn_launches = n[1];
   return 0;
 }
 

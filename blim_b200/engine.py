@@ -108,28 +108,33 @@ class Engine:
             pass
 
     # ---------------------------------------------------------------- weights
-    def load_state_dict(self, state_dict, rope_table_dtype=torch.bfloat16):
-        """Load parameters by their reference state_dict names; returns the list of ignored keys."""
-        ignored = []
+    def load_weight(self, name, t):
+        """One parameter by its reference state_dict name; returns False if the name is not on the scoring path."""
+        if not torch.is_tensor(t) or t.dtype not in _DTYPE_CODE:
+            return False
         with torch.cuda.device(self.device):
-            for name, t in state_dict.items():
-                if not torch.is_tensor(t) or t.dtype not in _DTYPE_CODE:
-                    ignored.append(name)
-                    continue
-                src = self._dev(t)
-                shape = (ctypes.c_int64 * src.dim())(*src.shape)
-                rc = self.lib.blim_load_weight(self.h, name.encode(), ctypes.c_void_p(src.data_ptr()), _DTYPE_CODE[src.dtype], shape,
-                                               src.dim(), self._stream())
-                if rc == 2:
-                    ignored.append(name)
-                elif rc != 0:
-                    self._check(rc)
-                del src
-            cos, sin = rope_tables(self.cfg.head_dim, self.cfg.rope_theta, self.cfg.max_positions, rope_table_dtype)
+            src = self._dev(t)
+            shape = (ctypes.c_int64 * src.dim())(*src.shape)
+            rc = self.lib.blim_load_weight(self.h, name.encode(), ctypes.c_void_p(src.data_ptr()), _DTYPE_CODE[src.dtype], shape, src.dim(),
+                                           self._stream())
+            if rc == 2:
+                return False
+            self._check(rc)
+            torch.cuda.current_stream(self.device).synchronize()  # src may be a temporary
+        return True
+
+    def set_rope(self, table_dtype=torch.bfloat16):
+        with torch.cuda.device(self.device):
+            cos, sin = rope_tables(self.cfg.head_dim, self.cfg.rope_theta, self.cfg.max_positions, table_dtype)
             cos, sin = self._dev(cos), self._dev(sin)
             self._check(self.lib.blim_set_rope(self.h, ctypes.c_void_p(cos.data_ptr()), ctypes.c_void_p(sin.data_ptr()),
                                                self.cfg.max_positions, self._stream()))
             torch.cuda.synchronize(self.device)
+
+    def load_state_dict(self, state_dict, rope_table_dtype=torch.bfloat16):
+        """Load parameters by their reference state_dict names; returns the list of ignored keys."""
+        ignored = [name for name, t in state_dict.items() if not self.load_weight(name, t)]
+        self.set_rope(rope_table_dtype)
         return ignored
 
     # ---------------------------------------------------------------- corpus
@@ -274,6 +279,16 @@ class Engine:
 
     def gemm_flops(self):
         return float(self.lib.blim_gemm_flops(self.h))
+
+    def profile(self, enable=True):
+        self._check(self.lib.blim_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        """-> dict(gemm_ms, attn_ms, gemm_launches, attn_launches) since the last read (synchronises the device)."""
+        g, a = ctypes.c_double(), ctypes.c_double()
+        ng, na = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self.lib.blim_profile_read(self.h, ctypes.byref(g), ctypes.byref(a), ctypes.byref(ng), ctypes.byref(na)))
+        return dict(gemm_ms=g.value, attn_ms=a.value, gemm_launches=ng.value, attn_launches=na.value)
 
     def debug_gemm(self, epilogue, A, W, bias=None, target=None, scale=1.0, cta_group=0, C=None):
         """Unit-test entry for the tcgen05 GEMM core (see blim_debug_gemm)."""

@@ -1,0 +1,139 @@
+"""Host-side stand-in for the reference model object, backed by the CUDA engine.
+
+`BlimModel` offers the attributes retrieval_utils.py touches on `model` / `model.module` (reference
+retrieval_utils.py:66,93,105,210): prepare_inputs_labels_for_multimodal, forward_visual, set_tvg_prefix_length and
+__call__(inputs_embeds=, attention_mask=) returning an object with .logits / .hidden_states.  That literal path
+materialises logits and exists for compatibility and testing; the fast path is blim_b200.retrieval, which hands whole
+pair lists to Engine.score_pairs.
+"""
+from types import SimpleNamespace
+
+import torch
+
+from .engine import Engine, ModelConfig, TEXTS_TVG, TEXTS_VTG
+
+IGNORE_INDEX = -100
+IMAGE_TOKEN_INDEX = -200
+
+
+class BlimModel:
+    def __init__(self, cfg: ModelConfig, state_dict=None, device=0, **engine_kw):
+        self.config = cfg
+        self.engine = Engine(cfg, device=device, **engine_kw)
+        self.device = self.engine.device
+        self.module = self  # DDP-style access used by the reference (model.module....)
+        self.tvg_prefix_length = 21
+        self._corpus_keys = {}
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # ------------------------------------------------------------------ nn.Module-ish surface
+    def load_state_dict(self, state_dict, strict=False):
+        return self.engine.load_state_dict(state_dict)
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def half(self):
+        return self
+
+    def set_tvg_prefix_length(self, n):
+        """modeling_videochat_flash.py:592"""
+        self.tvg_prefix_length = int(n)
+        self.engine.set_tvg_prefix_length(int(n))
+
+    def set_video_vocab(self, video_vocab):
+        """modeling_videochat_flash.py:589"""
+        self.video_vocab = video_vocab
+
+    def forward_visual(self, visual_token_embeds):
+        """modeling_videochat_flash.py:598-599"""
+        shp = visual_token_embeds.shape
+        out = self.engine.forward_visual(visual_token_embeds.reshape(-1, shp[-1]))
+        return out.reshape(*shp[:-1], -1).to(visual_token_embeds.dtype)
+
+    def __call__(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None, labels=None,
+                 **unused):
+        """VideoChatFlashQwenForCausalLM.forward as called on the scoring path (modeling_videochat_flash.py:601-629):
+        model(inputs_embeds=..., attention_mask=...)."""
+        if inputs_embeds is None:
+            raise NotImplementedError("the scoring path always passes inputs_embeds (retrieval_utils.py:93-103)")
+        logits, hidden = self.engine.forward_logits(inputs_embeds, attention_mask)
+        return SimpleNamespace(logits=logits, hidden_states=hidden.to(inputs_embeds.dtype), loss=None, past_key_values=None, attentions=None)
+
+    forward = __call__
+
+    # ------------------------------------------------------------------ multimodal glue (compat path)
+    def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels, images,
+                                             modalities=["image"], image_sizes=None, video_feature=False, tvg=False, cpn=False):
+        """video_feature=True branch of modeling_videochat_flash.py:185-515 with the projector and the embedding lookup
+        running in the engine.  Returns the reference's 6-tuple."""
+        assert video_feature, "only pre-extracted video features are on the scoring path"
+        dev = self.device
+        cfg = self.config
+        B = input_ids.shape[0]
+        feats = torch.stack([x.to(dev) for x in images], 0)                    # [B, n_clips, 64, MM]
+        n_clips, tpc = feats.shape[1], feats.shape[2]
+        proj = self.engine.project_video(feats.reshape(-1, feats.shape[-1]), tvg=tvg).reshape(B, n_clips, tpc, cfg.hidden_size)
+        vis = proj.float().mean(2).to(torch.bfloat16) if tvg else proj.reshape(B, n_clips * tpc, cfg.hidden_size)
+        seqs, labs, cpns = [], [], []
+        for b in range(B):
+            keep = attention_mask[b].bool()
+            ids, lab = input_ids[b][keep], labels[b][keep]
+            pos = (ids == IMAGE_TOKEN_INDEX).nonzero().flatten().tolist()
+            assert len(pos) == 1
+            i = pos[0]
+            left, right = ids[:i], ids[i + 1:]
+            emb = torch.cat([self.engine.embed_tokens(left), vis[b], self.engine.embed_tokens(right)], 0)
+            nv = vis[b].shape[0]
+            labs.append(torch.cat([lab[:i], torch.full((nv,), IGNORE_INDEX, dtype=lab.dtype, device=lab.device), lab[i + 1:]]))
+            if tvg:
+                m_left = torch.zeros(i, dtype=attention_mask.dtype, device=dev)
+                m_left[:self.tvg_prefix_length] = 1
+                m_vis = torch.ones(nv, dtype=attention_mask.dtype, device=dev)
+            else:
+                m_left = torch.ones(i, dtype=attention_mask.dtype, device=dev)
+                m_vis = torch.zeros(nv, dtype=attention_mask.dtype, device=dev)
+            cpns.append(torch.cat([m_left, m_vis, torch.ones(right.shape[0], dtype=attention_mask.dtype, device=dev)]))
+            seqs.append(emb)
+        L = max(s.shape[0] for s in seqs)
+        embeds = torch.zeros(B, L, cfg.hidden_size, dtype=torch.bfloat16, device=dev)
+        new_labels = torch.full((B, L), IGNORE_INDEX, dtype=labels.dtype, device=dev)
+        mask = torch.zeros(B, L, dtype=attention_mask.dtype, device=dev)
+        cpn_mask = torch.zeros(B, L, dtype=attention_mask.dtype, device=dev)
+        for b in range(B):
+            n = seqs[b].shape[0]
+            embeds[b, :n], new_labels[b, :n], mask[b, :n], cpn_mask[b, :n] = seqs[b], labs[b].to(dev), 1, cpns[b]
+        if cpn:
+            return None, None, (mask, cpn_mask), past_key_values, embeds, new_labels
+        return None, None, mask, past_key_values, embeds, new_labels
+
+    # ------------------------------------------------------------------ corpus registration for the fast path
+    def ensure_videos(self, video):
+        key = ("video", id(video), len(video))
+        if self._corpus_keys.get("video") != key:
+            feats = video if torch.is_tensor(video) else torch.stack(list(video), 0)
+            self.engine.set_videos(feats)
+            self._corpus_keys["video"] = key
+            self._corpus_keys.pop("vocab", None)
+
+    def ensure_texts(self, which, input_ids, attention_masks, labels):
+        key = (which, id(input_ids), id(labels), tuple(input_ids.shape) if torch.is_tensor(input_ids) else len(input_ids))
+        if self._corpus_keys.get(("texts", which)) != key:
+            if torch.is_tensor(input_ids):   # padded [N, Lmax] + masks (padding_ids output, retrieval_utils.py:155-167)
+                m = attention_masks.bool().cpu()
+                ids_l = [input_ids[i].cpu()[m[i]] for i in range(input_ids.shape[0])]
+                lab_l = [labels[i].cpu()[m[i]] for i in range(labels.shape[0])]
+            else:
+                ids_l, lab_l = list(input_ids), list(labels)
+            self.engine.set_texts(which, ids_l, lab_l)
+            self._corpus_keys[("texts", which)] = key
+
+    def ensure_vocab(self, video_vocab, tvg_video_labels):
+        key = ("vocab", id(video_vocab), id(tvg_video_labels))
+        if self._corpus_keys.get("vocab") != key:
+            self.engine.set_video_vocab(video_vocab, torch.as_tensor(tvg_video_labels).cpu().numpy())
+            self._corpus_keys["vocab"] = key

@@ -1,0 +1,245 @@
+"""Drop-in mirror of the reference's retrieval_utils.py (same names, argument lists, return values) on top of the
+CUDA engine.
+
+    evaluation(model, data_loader, device, tokenizer, args)                      reference retrieval_utils.py:170
+    compute_v2t_scores_x / compute_t2v_scores_x (same 14 parameters)             reference retrieval_utils.py:48 / 113
+    padding_ids(input_ids, labels, masks, tokenizer)                             reference retrieval_utils.py:155
+
+Differences in HOW (not in WHAT): a row's top-k candidates are not pushed through per-row padded batches; all rows'
+(video, text) pairs go to Engine.score_pairs in one call, which shares video / text prefixes and never materialises the
+logits.  evaluation() additionally scores each distinct (video, text) pair once for both directions and shards the
+pairs by video over the ranks, combining them with one all-gather of compact scores instead of dense all-reduces
+(reference retrieval_utils.py:252-262).
+"""
+import datetime
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .engine import TEXTS_TVG, TEXTS_VTG, TVG, TVG_PRIOR, VTG, VTG_PRIOR
+
+IGNORE_INDEX = -100
+
+
+def padding_ids(input_ids, labels, masks, tokenizer=None):
+    """LEFT-pad ragged id / label / mask lists to the global maximum (reference retrieval_utils.py:155-167)."""
+    n = len(input_ids)
+    width = max(len(x) for x in input_ids)
+    pad_id = tokenizer.pad_token_id if tokenizer is not None else 0
+    ids_p = torch.full((n, width), pad_id, dtype=torch.long)
+    lab_p = torch.full((n, width), IGNORE_INDEX, dtype=torch.long)
+    msk_p = torch.zeros((n, width), dtype=torch.long)
+    for i in range(n):
+        m = len(input_ids[i])
+        ids_p[i, width - m:] = input_ids[i]
+        lab_p[i, width - m:] = labels[i]
+        msk_p[i, width - m:] = masks[i]
+    return ids_p, lab_p, msk_p
+
+
+def _engine_model(model):
+    m = getattr(model, "module", model)
+    if not hasattr(m, "engine"):
+        raise TypeError("blim_b200.retrieval needs a blim_b200.model.BlimModel (CUDA engine); there is no PyTorch fallback")
+    return m
+
+
+def _rows_topk(iterator, topk, device):
+    rows = [r if torch.is_tensor(r) else torch.as_tensor(r) for r in iterator]
+    if not rows:
+        return None
+    sims = torch.stack(rows, 0).to(device)
+    k = min(sims.shape[1], topk)
+    return sims.topk(k=k, dim=1).indices  # [rows, k], same per-row result as sims.topk(k, dim=0) (ru:52,117)
+
+
+def _score_rows(scores_x, iterator, start, input_ids, attention_masks, labels, video, video_vocab, tvg_video_labels, model, device, args,
+                forward_type, cpn, rows_are_videos):
+    m = _engine_model(model)
+    eng = m.engine
+    idx = _rows_topk(iterator, args.topk, eng.device)
+    if idx is None:
+        return scores_x
+    n_rows, k = idx.shape
+    which = TEXTS_TVG if forward_type == "tvg" else TEXTS_VTG
+    m.ensure_videos(video)
+    m.ensure_texts(which, input_ids, attention_masks, labels)
+    if forward_type == "tvg":
+        m.ensure_vocab(video_vocab, tvg_video_labels)
+    kind = {("vtg", False): VTG, ("vtg", True): VTG_PRIOR, ("tvg", False): TVG, ("tvg", True): TVG_PRIOR}[(forward_type, bool(cpn))]
+    rows = torch.arange(start, start + n_rows, device=idx.device)[:, None].expand(n_rows, k).reshape(-1)
+    cols = idx.reshape(-1)
+    pv, pt = (rows, cols) if rows_are_videos else (cols, rows)
+    scores = eng.score_pairs(kind, pv.cpu().numpy(), pt.cpu().numpy())
+    scores_x[rows.to(scores_x.device), cols.to(scores_x.device)] = scores.to(scores_x.device, scores_x.dtype)
+    return scores_x
+
+
+def compute_v2t_scores_x(v2t_scores_x, iterator, start, input_ids, attention_masks, labels, video, video_vocab, tvg_video_labels, model,
+                         device, args, forward_type=None, cpn=False):
+    """Video -> text rows: row `start + i` is a video, its top-k texts are scored (reference retrieval_utils.py:48-111)."""
+    return _score_rows(v2t_scores_x, iterator, start, input_ids, attention_masks, labels, video, video_vocab, tvg_video_labels, model,
+                       device, args, forward_type, cpn, rows_are_videos=True)
+
+
+def compute_t2v_scores_x(t2v_scores_x, iterator, start, input_ids, attention_masks, labels, video, video_vocab, tvg_video_labels, model,
+                         device, args, forward_type=None, cpn=False):
+    """Text -> video rows: row `start + i` is a text, its top-k videos are scored (reference retrieval_utils.py:113-153)."""
+    return _score_rows(t2v_scores_x, iterator, start, input_ids, attention_masks, labels, video, video_vocab, tvg_video_labels, model,
+                       device, args, forward_type, cpn, rows_are_videos=False)
+
+
+# ------------------------------------------------------------------------------------------------ evaluation
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _all_gather_var(t, world):
+    """All-gather of a 1-D tensor whose length differs per rank (pad to the maximum, one collective per call)."""
+    n = torch.tensor([t.numel()], device=t.device, dtype=torch.long)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    width = max(sizes)
+    buf = torch.zeros(width, device=t.device, dtype=t.dtype)
+    buf[:t.numel()] = t
+    out = torch.empty(world * width, device=t.device, dtype=t.dtype)
+    dist.all_gather_into_tensor(out, buf)
+    return torch.cat([out[r * width:r * width + sizes[r]] for r in range(world)])
+
+
+class PairPlan:
+    """Candidate pairs of one evaluation: per direction the top-k index arrays, plus the deduplicated union."""
+
+    def __init__(self, v2t_iv2, t2v_iv2, topk, device):
+        self.v2t_idx = v2t_iv2.to(device).topk(k=min(v2t_iv2.shape[1], topk), dim=1).indices  # [Nv, k] text ids
+        self.t2v_idx = t2v_iv2.to(device).topk(k=min(t2v_iv2.shape[1], topk), dim=1).indices  # [Nt, k] video ids
+        nv, k = self.v2t_idx.shape
+        nt = self.t2v_idx.shape[0]
+        self.n_videos, self.n_texts, self.k = nv, nt, k
+        v_a = torch.arange(nv, device=device)[:, None].expand(nv, k).reshape(-1)
+        t_a = self.v2t_idx.reshape(-1)
+        t_b = torch.arange(nt, device=device)[:, None].expand(nt, self.t2v_idx.shape[1]).reshape(-1)
+        v_b = self.t2v_idx.reshape(-1)
+        self.v2t_pairs = (v_a, t_a)   # entries of the v2t matrices  [v, t]
+        self.t2v_pairs = (v_b, t_b)   # entries of the t2v matrices  [t, v]
+        key = torch.cat([v_a * nt + t_a, v_b * nt + t_b])
+        self.union_key, inverse = torch.unique(key, return_inverse=True)  # sorted by (video, text)
+        self.v2t_in_union = inverse[:v_a.numel()]
+        self.t2v_in_union = inverse[v_a.numel():]
+        self.union_v = torch.div(self.union_key, nt, rounding_mode="floor")
+        self.union_t = self.union_key - self.union_v * nt
+
+
+def score_all(model, plan: PairPlan, cpn=True, full=True, distributed=False):
+    """Scores every term evaluation() needs on the deduplicated pair set.  Multi-GPU: the pairs are sharded by the id
+    that owns the shared prefix (each video / text prefix is prefilled on exactly one rank), one all-gather per score
+    kind of compact fp32 scores.
+    Returns a dict of compact device tensors aligned with plan.union_* (vtg, tvg) / plan.v2t_pairs (vtg_prior) /
+    plan.t2v_pairs (tvg_prior)."""
+    m = _engine_model(model)
+    eng = m.engine
+    rank, world = _world() if distributed else (0, 1)
+
+    def run(kind, pv, pt):
+        if world == 1:
+            return eng.score_pairs(kind, pv.cpu().numpy(), pt.cpu().numpy())
+        # shard by the id that owns the shared prefix: video for VTG / TVG prior, text for VTG prior / TVG
+        owner = pv if kind in (VTG, TVG_PRIOR) else pt
+        mine = (owner % world) == rank
+        sel = mine.nonzero().flatten()
+        local = eng.score_pairs(kind, pv[sel].cpu().numpy(), pt[sel].cpu().numpy())
+        all_scores = _all_gather_var(local, world)
+        all_sel = _all_gather_var(sel, world)
+        out = torch.empty(pv.numel(), dtype=torch.float32, device=eng.device)
+        out[all_sel] = all_scores
+        return out
+
+    out = {"vtg": run(VTG, plan.union_v, plan.union_t)}
+    if cpn:
+        out["vtg_prior"] = run(VTG_PRIOR, *plan.v2t_pairs)
+    if full:
+        out["tvg"] = run(TVG, plan.union_v, plan.union_t)
+        if cpn:
+            out["tvg_prior"] = run(TVG_PRIOR, *plan.t2v_pairs)
+    return out
+
+
+def compact_terms(plan: PairPlan, s, cpn=True, full=True):
+    """[rows, k] arrays per direction in the reference's vocabulary (retrieval_utils.py:264-276)."""
+    nv, nt = plan.n_videos, plan.n_texts
+    v2t = {"idx": plan.v2t_idx, "candidate_likelihood": s["vtg"][plan.v2t_in_union].view(nv, -1)}
+    t2v = {"idx": plan.t2v_idx, "query_likelihood": s["vtg"][plan.t2v_in_union].view(nt, -1)}
+    if cpn:
+        v2t["candidate_prior"] = s["vtg_prior"].view(nv, -1)
+    if full:
+        v2t["query_likelihood"] = s["tvg"][plan.v2t_in_union].view(nv, -1)
+        t2v["candidate_likelihood"] = s["tvg"][plan.t2v_in_union].view(nt, -1)
+        if cpn:
+            t2v["candidate_prior"] = s["tvg_prior"].view(nt, -1)
+    return t2v, v2t
+
+
+def dense_matrices(eng, compact, n_rows, n_cols):
+    """-100-filled dense matrices with the candidate entries scattered in (reference retrieval_utils.py:219,110,152)."""
+    idx = compact["idx"]
+    rows = torch.arange(n_rows, device=idx.device)[:, None].expand_as(idx).reshape(-1)
+    out = {}
+    for name, val in compact.items():
+        if name == "idx":
+            continue
+        out[name] = eng.scatter_scores(n_rows, n_cols, rows, idx.reshape(-1), val.reshape(-1))
+    return out
+
+
+@torch.no_grad()
+def evaluation(model, data_loader, device, tokenizer, args):
+    """Same contract as the reference's evaluation() (retrieval_utils.py:169-281): returns (t2v_dict, v2t_dict) of numpy
+    fp32 matrices under the keys candidate_likelihood / query_likelihood / internvideo2 / candidate_prior.
+    The InternVideo2 scores come from `./scores/{dataset}[_zeroshot].pth` like in the reference, or from
+    `args.iv2_scores = {"v2t": ..., "t2v": ...}` when present (synthetic runs)."""
+    m = _engine_model(model)
+    eng = m.engine
+    start_time = time.time()
+    video, tvg_video_labels = [], []
+    vtg_ids, vtg_labels, vtg_masks = [], [], []
+    tvg_ids, tvg_labels, tvg_masks = [], [], []
+    for data in data_loader:                                           # retrieval_utils.py:182-193
+        video += [v for v in data["video"]]
+        vtg_ids += data["vtg_ids"]; vtg_labels += data["vtg_labels"]; vtg_masks += data["vtg_masks"]
+        tvg_ids += data["tvg_ids"]; tvg_labels += data["tvg_labels"]; tvg_masks += data["tvg_masks"]
+        tvg_video_labels.append(data["tvg_video_labels"])
+    tvg_video_labels = torch.cat(tvg_video_labels, dim=0)
+    zero_shot = args.resume == "" and args.eval                         # retrieval_utils.py:199
+    scores = getattr(args, "iv2_scores", None)
+    if scores is None:
+        name = f"./scores/{args.dataset.lower()}_zeroshot.pth" if zero_shot else f"./scores/{args.dataset.lower()}.pth"
+        scores = torch.load(name, weights_only=True)
+    v2t_iv2, t2v_iv2 = scores["v2t"], scores["t2v"]
+    num_texts, num_videos = t2v_iv2.shape
+    full = not zero_shot
+
+    # pad-stripped ragged texts go straight to the engine (padding_ids + the mask strip of mvf:333-334 cancel out)
+    strip = lambda xs, ms: [x[mk.bool()] for x, mk in zip(xs, ms)]
+    m.ensure_videos(video)
+    eng.set_texts(TEXTS_VTG, strip(vtg_ids, vtg_masks), strip(vtg_labels, vtg_masks))
+    eng.set_texts(TEXTS_TVG, strip(tvg_ids, tvg_masks), strip(tvg_labels, tvg_masks))
+    if full:
+        m.ensure_vocab(data_loader.dataset.video_vocab, tvg_video_labels)
+    m.set_tvg_prefix_length(data_loader.dataset.tvg_prefix_length)      # retrieval_utils.py:210
+
+    plan = PairPlan(v2t_iv2.float(), t2v_iv2.float(), args.topk, eng.device)
+    s = score_all(model, plan, cpn=bool(args.cpn), full=full, distributed=bool(getattr(args, "distributed", False)))
+    t2v_c, v2t_c = compact_terms(plan, s, cpn=bool(args.cpn), full=full)
+    m.last_plan, m.last_compact = plan, (t2v_c, v2t_c)                  # kept on the device for the fused rerank
+
+    t2v_dict = {k: v.cpu().numpy() for k, v in dense_matrices(eng, t2v_c, num_texts, num_videos).items()}
+    v2t_dict = {k: v.cpu().numpy() for k, v in dense_matrices(eng, v2t_c, num_videos, num_texts).items()}
+    t2v_dict["internvideo2"] = t2v_iv2.cpu().numpy()
+    v2t_dict["internvideo2"] = v2t_iv2.cpu().numpy()
+    print(f"Evaluation time {str(datetime.timedelta(seconds=int(time.time() - start_time)))}")
+    return t2v_dict, v2t_dict

@@ -67,28 +67,31 @@ def param_shapes(cfg: ModelConfig):
     return shapes
 
 
+def init_weight(cfg: ModelConfig, name, idx, seed=0, device="cpu", std=0.02, rich=False, dtype=torch.bfloat16):
+    """One parameter of init_weights (generated from (seed, idx): tensors can be streamed one at a time)."""
+    shape = param_shapes(cfg)[name]
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed * 100003 + idx)
+    if name.endswith("norm.weight") or name.endswith("layernorm.weight"):
+        t = torch.ones(shape, device=dev)
+        if rich:
+            t = t + 0.1 * torch.randn(shape, generator=g, device=dev)
+    elif name.endswith(".bias"):
+        t = torch.zeros(shape, device=dev)
+        if rich:
+            t = 0.5 * std * torch.randn(shape, generator=g, device=dev)
+    else:
+        t = torch.randn(shape, generator=g, device=dev, dtype=torch.float32 if dev.type == "cpu" else dtype) * std
+    return t.to(dtype)
+
+
 def init_weights(cfg: ModelConfig, seed=0, device="cpu", std=0.02, rich=False, dtype=torch.bfloat16):
     """Random parameters.  rich=False follows the reference's _init_weights (modeling_qwen2_flash.py:834-843): N(0, std)
     Linear / Embedding weights, zero biases, unit RMSNorm weights.  rich=True also randomises biases and norm weights so
     that every term of the path is exercised by parity tests.  Values are generated per tensor from (seed, index) in
     fp32 and rounded to `dtype`, so the engine and the oracle see identical, bf16-representable numbers."""
-    out = {}
-    dev = torch.device(device)
-    for idx, (name, shape) in enumerate(param_shapes(cfg).items()):
-        g = torch.Generator(device=dev)
-        g.manual_seed(seed * 100003 + idx)
-        if name.endswith("norm.weight") or name.endswith("layernorm.weight"):
-            t = torch.ones(shape, device=dev)
-            if rich:
-                t = t + 0.1 * torch.randn(shape, generator=g, device=dev)
-        elif name.endswith(".bias"):
-            t = torch.zeros(shape, device=dev)
-            if rich:
-                t = 0.5 * std * torch.randn(shape, generator=g, device=dev)
-        else:
-            t = torch.randn(shape, generator=g, device=dev, dtype=torch.float32 if dev.type == "cpu" else dtype) * std
-        out[name] = t.to(dtype)
-    return out
+    return {name: init_weight(cfg, name, idx, seed, device, std, rich, dtype) for idx, name in enumerate(param_shapes(cfg))}
 
 
 @dataclass

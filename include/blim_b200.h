@@ -41,7 +41,7 @@ typedef struct blim_model_cfg {
   float rms_norm_eps;
   int32_t max_run_tokens;    /* workspace: tokens per decoder run (0 = default 32768) */
   int32_t max_prefix_tokens; /* workspace: rows of the shared-prefix KV cache (0 = default 32768) */
-  int32_t gemm_cta_group;    /* 1 = one CTA per 128x256 tile, 2 = CTA pairs (cta_group::2, 256x256 tiles); 0 = default */
+  int32_t gemm_cta_group;    /* 1 = one CTA per 128x256 tile, 2 = CTA pairs (cta_group::2, 256x256 tiles); 0 = default (2) */
 } blim_model_cfg;
 
 /* Score kinds of blim_score_pairs.
@@ -128,6 +128,12 @@ int blim_scatter_scores(blim_engine* e, float* dense, int n_rows, int n_cols, in
 /* Counters for bench.py: kernels launched by this engine since creation / FLOPs of its tensor-core GEMMs. */
 int64_t blim_kernel_launches(const blim_engine* e);
 double blim_gemm_flops(const blim_engine* e);
+
+/* Measurement support for bench.py: with profiling enabled every tcgen05 GEMM / attention launch is bracketed by CUDA
+ * events on the launching stream; blim_profile_read synchronises the device, returns the summed device time and launch
+ * count per kernel family since the last read, and resets. */
+int blim_profile(blim_engine* e, int enable);
+int blim_profile_read(blim_engine* e, double* gemm_ms, double* attn_ms, int64_t* gemm_launches, int64_t* attn_launches);
 
 /* Debug / unit-test entry: C = epilogue(A[M,K] · W[N,K]^T) with the engine's tcgen05 GEMM.
  * epilogue: 0 = bf16 store, 1 = bf16 store + bias, 2 = bf16 store + bias + GELU, 3 = fp32 store,

@@ -100,7 +100,7 @@ def test_forward_logits_matches_oracle(cfg_name, cg):
         assert eh <= 3e-2 * scale_h and el <= 3e-2 * scale_l, f"hidden err {eh} (scale {scale_h}), logits err {el} (scale {scale_l})"
         # log-softmax of the logits is what the scores are made of
         lp = (torch.log_softmax(logits, -1) - torch.log_softmax(ref_logits, -1)).abs().max().item()
-        assert lp < 5e-2, lp
+        assert lp < 5e-2 * max(1.0, scale_l), (lp, scale_l)
     finally:
         eng.close()
 
