@@ -314,6 +314,7 @@ def main():
     eng.profile(True)
     eng.profile_read()
     launches0 = eng.kernel_launches()
+    flops0 = eng.gemm_flops()
     sampler = ClockSampler(local_rank)
     sampler.start()
     total_ms, (res, plan) = timed(step_device, args.steps)
@@ -321,6 +322,7 @@ def main():
     prof = eng.profile_read()
     eng.profile(False)
     launches = (eng.kernel_launches() - launches0) // max(1, args.steps)
+    executed_flops = (eng.gemm_flops() - flops0) / args.steps
     pairs = 2 * n * topk
     ms_per_step = total_ms / args.steps
     value = pairs / (ms_per_step / 1000.0)
@@ -335,7 +337,7 @@ def main():
                 "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": None,
                 "peak_source": f"{peaks['source']} (sustained cuBLAS bf16; burst {peaks['bf16_burst']})",
                 "algorithmic_gemm_flops_per_step": f_gemm, "algorithmic_attention_flops_per_step": f_attn,
-                "executed_gemm_flops_per_step": None, "gemm_launches_per_step": prof["gemm_launches"] // max(1, args.steps),
+                "executed_gemm_flops_per_step": executed_flops, "gemm_launches_per_step": prof["gemm_launches"] // max(1, args.steps),
                 "gemm_ms_per_step": prof["gemm_ms"] / args.steps, "attention_ms_per_step": prof["attn_ms"] / args.steps,
                 "gemm_share_of_step": prof["gemm_ms"] / total_ms, "attention_share_of_step": prof["attn_ms"] / total_ms,
                 "whole_step_tflops": (f_gemm + f_attn) * share / (ms_per_step / 1000.0) / 1e12}

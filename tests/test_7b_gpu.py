@@ -1,0 +1,101 @@
+"""Full-size (VideoChat-Flash-Qwen2-7B architecture, random init) parity and property tests.  GPU only, ~2 minutes.
+
+ * engine vs the oracle (reference algorithm restated in plain PyTorch, fp32, run on the GPU for speed) on a handful of
+   pairs of every score kind: |d log-likelihood| <= 1e-2 (BASELINE.json north_star tolerance for the bf16 pipeline);
+ * size-independent properties on MSRVTT-shaped data: re-batching invariance (a pair's score does not depend on
+   which other pairs share its decoder run) and direction symmetry of the deduplicated pair set."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from blim_b200 import synth
+from blim_b200.engine import TVG, TVG_PRIOR, VTG, VTG_PRIOR, ModelConfig
+from blim_b200.model import BlimModel
+from oracle import blim_oracle as O
+
+KIND = {("vtg", False): VTG, ("vtg", True): VTG_PRIOR, ("tvg", False): TVG, ("tvg", True): TVG_PRIOR}
+
+
+@pytest.fixture(scope="module")
+def seven_b():
+    cfg = ModelConfig.qwen2_7b()
+    dev = torch.device("cuda", 0)
+    model = BlimModel(cfg, device=0)
+    shapes = synth.param_shapes(cfg)
+    weights = {}
+    for idx, name in enumerate(shapes):
+        t = synth.init_weight(cfg, name, idx, seed=0, device=dev, std=0.02, rich=True)
+        model.engine.load_weight(name, t)
+        weights[name] = t
+    model.engine.set_rope(torch.bfloat16)
+    yield cfg, model, weights
+    model.engine.close()
+
+
+def _set_corpus(model, corpus):
+    eng = model.engine
+    eng.set_videos(corpus.video)
+    eng.set_texts(0, corpus.vtg_ids, corpus.vtg_labels)
+    eng.set_texts(1, corpus.tvg_ids, corpus.tvg_labels)
+    eng.set_video_vocab(corpus.video_vocab, corpus.tvg_video_labels.numpy())
+    model.set_tvg_prefix_length(corpus.tvg_prefix_length)
+
+
+def test_7b_scores_match_oracle(seven_b):
+    cfg, model, weights = seven_b
+    corpus = synth.make_corpus(cfg, "msrvtt", n=6, seed=5)
+    _set_corpus(model, corpus)
+    p = {k: v.float() for k, v in weights.items()}   # fp32 copy of the same bf16 values (~30 GB)
+    worst = {}
+    try:
+        for direction in ("v2t", "t2v"):
+            for ft, cpn in (("vtg", False), ("vtg", True), ("tvg", False), ("tvg", True)):
+                with torch.no_grad():
+                    ref = O.compute_scores_x(p, cfg, corpus, direction, ft, cpn, topk=2, batch_size=2, rows=[0, 4], device="cuda").numpy()
+                rows, cols = np.nonzero(ref != -100.0)
+                pv, pt = (rows, cols) if direction == "v2t" else (cols, rows)
+                got = model.engine.score_pairs(KIND[(ft, cpn)], pv, pt).cpu().numpy()
+                err = float(np.abs(got - ref[rows, cols]).max())
+                worst[(direction, ft, cpn)] = err
+                assert np.isfinite(got).all()
+                assert err <= 1e-2, f"{direction} {ft} cpn={cpn}: |d|={err} got {got} want {ref[rows, cols]}"
+    finally:
+        del p
+        torch.cuda.empty_cache()
+    print("7B max |d| per kind:", worst)
+
+
+def test_7b_rebatching_invariance_and_symmetry(seven_b):
+    cfg, model, weights = seven_b
+    corpus = synth.make_corpus(cfg, "msrvtt", n=96, seed=9, feat_device="cuda")
+    _set_corpus(model, corpus)
+    from blim_b200.retrieval import PairPlan, score_all, compact_terms
+    plan = PairPlan(corpus.v2t_iv2, corpus.t2v_iv2, 8, model.device)
+    s = score_all(model, plan, cpn=True, full=True)
+    uv, ut = plan.union_v.cpu().numpy(), plan.union_t.cpu().numpy()
+    rng = np.random.default_rng(0)
+    sel = rng.permutation(len(uv))[:40]
+    for kind, key in ((VTG, "vtg"), (TVG, "tvg")):
+        again = model.engine.score_pairs(kind, uv[sel], ut[sel]).cpu().numpy()     # different run composition, reversed order
+        full = s[key].cpu().numpy()[sel]
+        assert np.array_equal(again, full), f"{key}: scores depend on batch composition, max |d| {np.abs(again - full).max()}"
+    # direction symmetry through the dedupe: v2t[v,t] and t2v[t,v] are the same number wherever both exist
+    t2v_c, v2t_c = compact_terms(plan, s)
+    a = {(int(v), int(t)): float(x) for v, row, xs in zip(range(corpus.n), plan.v2t_idx.cpu().numpy(), v2t_c["candidate_likelihood"].cpu().numpy()) for t, x in zip(row, xs)}
+    n_both = 0
+    for t, row, xs in zip(range(corpus.n), plan.t2v_idx.cpu().numpy(), t2v_c["query_likelihood"].cpu().numpy()):
+        for v, x in zip(row, xs):
+            if (int(v), t) in a:
+                n_both += 1
+                assert a[(int(v), t)] == float(x)
+    assert n_both > 0
+    # the VTG prior is a function of the text only
+    pr = v2t_c["candidate_prior"].cpu().numpy()
+    idx = plan.v2t_idx.cpu().numpy()
+    by_text = {}
+    for r in range(corpus.n):
+        for t, x in zip(idx[r], pr[r]):
+            by_text.setdefault(int(t), set()).add(float(x))
+    assert all(len(v) == 1 for v in by_text.values())
