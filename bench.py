@@ -270,7 +270,7 @@ def main():
         if want_cpu:
             weights_cpu[name] = t.cpu()
         del t
-    eng.set_rope(torch.bfloat16)
+    eng.set_rope(torch.float32)
     corpus = synth.make_corpus(cfg, wl["dataset"], n=args.n or wl["n"], n_clips=wl["n_clips"], seed=1, feat_device=dev)
     n, topk = corpus.n, wl["topk"]
     alpha, c = wl["alpha"], wl["c"]

@@ -533,10 +533,7 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
   for (int p : run.tok_pos)
     if (p < 0 || p >= e->rope_n) return e->fail("sequence longer than the rotary table (max_positions)");
   std::vector<AttnWork> works;
-  for (size_t s = 0; s < run.seqs.size(); ++s) {
-    const int nb = (run.seqs[s].q_len * e->G + kAttnRows - 1) / kAttnRows;
-    for (int b = 0; b < nb; ++b) works.push_back(AttnWork{static_cast<int>(s), b});
-  }
+  build_attn_works(run.seqs.data(), static_cast<int>(run.seqs.size()), e->G, works);
   CKR(upload(e, e->d_tok_pos, run.tok_pos.data(), T * sizeof(int), st));
   CKR(upload(e, e->d_seqs, run.seqs.data(), run.seqs.size() * sizeof(AttnSeq), st));
   CKR(upload(e, e->d_works, works.data(), works.size() * sizeof(AttnWork), st));

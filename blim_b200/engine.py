@@ -48,10 +48,11 @@ class EngineError(RuntimeError):
     pass
 
 
-def rope_tables(head_dim, theta, n_positions, table_dtype=torch.bfloat16):
+def rope_tables(head_dim, theta, n_positions, table_dtype=torch.float32):
     """cos/sin [n_positions, head_dim/2] fp32, built like Qwen2RotaryEmbedding._set_cos_sin_cache
-    (reference modeling_qwen2_flash.py:109,119-127) including the cast of the cached tables to the model dtype
-    (modeling_qwen2_flash.py:133-134)."""
+    (reference modeling_qwen2_flash.py:109,119-127).  The reference casts the cached tables to the activation dtype
+    (modeling_qwen2_flash.py:133-134); table_dtype=torch.bfloat16 reproduces that rounding, the default keeps the fp32
+    tables (what the fp32 reference / oracle uses, and strictly closer to the exact rotation)."""
     inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))
     t = torch.arange(n_positions, dtype=torch.int64).type_as(inv_freq)
     freqs = torch.outer(t, inv_freq)
@@ -123,7 +124,7 @@ class Engine:
             torch.cuda.current_stream(self.device).synchronize()  # src may be a temporary
         return True
 
-    def set_rope(self, table_dtype=torch.bfloat16):
+    def set_rope(self, table_dtype=torch.float32):
         with torch.cuda.device(self.device):
             cos, sin = rope_tables(self.cfg.head_dim, self.cfg.rope_theta, self.cfg.max_positions, table_dtype)
             cos, sin = self._dev(cos), self._dev(sin)
@@ -131,7 +132,7 @@ class Engine:
                                                self.cfg.max_positions, self._stream()))
             torch.cuda.synchronize(self.device)
 
-    def load_state_dict(self, state_dict, rope_table_dtype=torch.bfloat16):
+    def load_state_dict(self, state_dict, rope_table_dtype=torch.float32):
         """Load parameters by their reference state_dict names; returns the list of ignored keys."""
         ignored = [name for name, t in state_dict.items() if not self.load_weight(name, t)]
         self.set_rope(rope_table_dtype)
