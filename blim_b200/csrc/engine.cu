@@ -206,11 +206,11 @@ static int gemm_qkv(blim_engine* e, const bf16* A, const LayerW& w, int M, bf16*
                     cudaStream_t st) {
   if (e->DH == 128) {
     EpiQkvRope<128>::Params p{q_out, k_out, v_out, w.b_qkv.as<float>(), pos, nullptr, e->rope_cos.as<float>(), e->rope_sin.as<float>(),
-                              e->NQ, e->NKVD};
+                              e->NQ, e->NKVD, e->rope_n};
     return gemm<EpiQkvRope<128>>(e, A, e->H, w.w_qkv.as<bf16>(), e->H, M, e->NQKV, e->H, p, st);
   }
   EpiQkvRope<64>::Params p{q_out, k_out, v_out, w.b_qkv.as<float>(), pos, nullptr, e->rope_cos.as<float>(), e->rope_sin.as<float>(),
-                           e->NQ, e->NKVD};
+                           e->NQ, e->NKVD, e->rope_n};
   return gemm<EpiQkvRope<64>>(e, A, e->H, w.w_qkv.as<bf16>(), e->H, M, e->NQKV, e->H, p, st);
 }
 
@@ -390,8 +390,12 @@ extern "C" int blim_set_rope(blim_engine* e, const float* cos_dev, const float* 
   const size_t bytes = static_cast<size_t>(n_positions) * (e->DH / 2) * 4;
   CKE(e->rope_cos.reserve(bytes));
   CKE(e->rope_sin.reserve(bytes));
-  CKE(cudaMemcpyAsync(e->rope_cos.p, cos_dev, bytes, cudaMemcpyDeviceToDevice, S(stream)));
-  CKE(cudaMemcpyAsync(e->rope_sin.p, sin_dev, bytes, cudaMemcpyDeviceToDevice, S(stream)));
+  // stored transposed: [head_dim/2][n_positions] (see EpiQkvRope)
+  const int n_el = n_positions * (e->DH / 2);
+  transpose_f32_kernel<<<(n_el + 255) / 256, 256, 0, S(stream)>>>(e->rope_cos.as<float>(), cos_dev, n_positions, e->DH / 2);
+  CKL();
+  transpose_f32_kernel<<<(n_el + 255) / 256, 256, 0, S(stream)>>>(e->rope_sin.as<float>(), sin_dev, n_positions, e->DH / 2);
+  CKL();
   e->rope_n = n_positions;
   return 0;
 }
@@ -579,10 +583,10 @@ static int lse_rows(blim_engine* e, const bf16* A, int lda, const bf16* W, int l
                     float* logp_dev, cudaStream_t st) {
   if (R <= 0) return 0;
   const int n_tiles = (N + kBN - 1) / kBN;
-  CKE(e->partial.reserve(static_cast<size_t>(e->Tmax) * n_tiles * sizeof(float2)));
+  CKE(e->partial.reserve(static_cast<size_t>(e->Tmax) * 2 * n_tiles * sizeof(float2)));
   EpiLse::Params p{e->partial.as<float2>(), e->tgt_logit.as<float>(), targets_dev, scale};
   CKR(gemm<EpiLse>(e, A, lda, W, ldw, R, N, K, p, st));
-  lse_finalize_kernel<<<(R + 7) / 8, 256, 0, st>>>(logp_dev, e->partial.as<float2>(), e->tgt_logit.as<float>(), R, n_tiles);
+  lse_finalize_kernel<<<(R + 7) / 8, 256, 0, st>>>(logp_dev, e->partial.as<float2>(), e->tgt_logit.as<float>(), R, 2 * n_tiles);
   CKL();
   return 0;
 }

@@ -11,7 +11,8 @@
 //   warp 0   TMA producer      : cp.async.bulk.tensor (SWIZZLE_128B) -> kStages-deep smem ring, mbarrier full/empty
 //   warp 1   MMA issuer        : one elected thread issues tcgen05.mma (M=128·cta_group, N=256, K=16), tcgen05.commit frees slots
 //   warp 2   TMEM allocator    : 512 columns = 2 accumulator stages of 256 fp32 columns
-//   warps 4-7 epilogue         : tcgen05.ld (one TMEM lane = one output row per thread) -> fused epilogue -> global
+//   warps 4-11 epilogue        : tcgen05.ld (one TMEM lane = one output row per thread) -> fused epilogue -> global;
+//                                two warpgroups, each owns half of the tile's columns (TMEM lane quadrant = warp % 4)
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1.
 #pragma once
 #include <cuda.h>
@@ -28,7 +29,7 @@ constexpr int kBM = 128;   // rows per CTA
 constexpr int kBN = 256;   // columns per tile (= one UMMA N)
 constexpr int kBK = 64;    // K per pipeline stage: 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;  // 4 control warps + 8 epilogue warps
 constexpr int kTmemCols = 512;
 
 template <int kCtaGroup>
@@ -107,8 +108,8 @@ __device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&v)[32]) {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // Every epilogue gets: this thread's global row (may be >= M: loads from TMEM still have to be executed warp-uniformly,
-// only the global-memory side is predicated), the tile's first column n0, and the TMEM address of (its lane, column 0
-// of the accumulator stage).
+// only the global-memory side is predicated), the tile's first column n0, the TMEM address of (its lane, column 0
+// of the accumulator stage) and `half` (0/1): which half of the tile's work this epilogue warpgroup owns.
 
 // out[row, col] = act(acc + bias[col])   OutT = __nv_bfloat16 or float
 template <typename OutT, bool kBias, bool kGelu>
@@ -118,10 +119,10 @@ struct EpiStore {
     int ldo;
     const float* bias;
   };
-  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr) {
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
     const bool row_ok = row < d.M;
 #pragma unroll 1
-    for (int c = 0; c < kBN; c += 32) {
+    for (int c = half * (kBN / 2); c < (half + 1) * (kBN / 2); c += 32) {
       float v[32];
       tmem_ld32f(taddr + c, v);
       const int col = n0 + c;
@@ -153,10 +154,10 @@ struct EpiResid {
     float* resid;
     int ldo;
   };
-  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr) {
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
     const bool row_ok = row < d.M;
 #pragma unroll 1
-    for (int c = 0; c < kBN; c += 32) {
+    for (int c = half * (kBN / 2); c < (half + 1) * (kBN / 2); c += 32) {
       float v[32];
       tmem_ld32f(taddr + c, v);
       const int col = n0 + c;
@@ -185,6 +186,10 @@ struct EpiResid {
 // Fused QKV projection epilogue: + bias, rotary embedding on Q and K heads (half-split rotation, per-token position
 // looked up in a host-built cos/sin table), Q -> q_out[token], K/V -> kv cache rows kv_slot[token].
 // Column layout of the fused weight: [ Q heads | K heads | V heads ], every head head_dim wide; kBN is a multiple of head_dim.
+// The table is stored transposed, [head_dim/2][max_pos]: consecutive tokens (= consecutive TMEM lanes = the lanes of a
+// warp) have consecutive positions, so one table load of a warp touches one or two 128 B lines instead of 32.
+// Work split between the two epilogue warpgroups: a tile holds 4 (32-wide rotary chunk, head) items; each warpgroup takes
+// the two items that share one rotary chunk (head_dim 128: chunk = half, both heads; head_dim 64: heads 2*half, 2*half+1).
 template <int kHeadDim>
 struct EpiQkvRope {
   struct Params {
@@ -194,22 +199,30 @@ struct EpiQkvRope {
     const float* bias;     // [n_q + 2 n_kv]
     const int* pos;        // [M] rotary position of each token
     const int* kv_slot;    // [M] cache row of each token (nullptr: row index)
-    const float* cos_tab;  // [max_pos, kHeadDim/2]
+    const float* cos_tab;  // [kHeadDim/2][max_pos]
     const float* sin_tab;
-    int n_q, n_kv;
+    int n_q, n_kv, max_pos;
   };
-  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr) {
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
     constexpr int kHalf = kHeadDim / 2;
+    static_assert(kHeadDim == 64 || kHeadDim == 128, "head_dim must be 64 or 128");
     const bool row_ok = row < d.M;
     int pos = 0, slot = 0;
     if (row_ok) {
       pos = __ldg(p.pos + row);
       slot = p.kv_slot ? __ldg(p.kv_slot + row) : row;
     }
-    const float* cosr = p.cos_tab + static_cast<size_t>(pos) * kHalf;
-    const float* sinr = p.sin_tab + static_cast<size_t>(pos) * kHalf;
+    const int j0 = (kHeadDim == 128) ? half * 32 : 0;          // rotary chunk inside the half-dim
+    const int head0 = (kHeadDim == 128) ? 0 : half * 2;        // first of the two heads this warpgroup handles
+    float cs[32], sn[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      cs[i] = __ldg(p.cos_tab + static_cast<size_t>(j0 + i) * p.max_pos + pos);
+      sn[i] = __ldg(p.sin_tab + static_cast<size_t>(j0 + i) * p.max_pos + pos);
+    }
 #pragma unroll 1
-    for (int h = 0; h < kBN / kHeadDim; ++h) {
+    for (int hh = 0; hh < 2; ++hh) {
+      const int h = head0 + hh;
       const int c0 = n0 + h * kHeadDim;  // first fused column of this head
       if (c0 >= d.N) break;              // warp-uniform
       __nv_bfloat16* dst;
@@ -224,29 +237,20 @@ struct EpiQkvRope {
         dst = p.v_out + static_cast<size_t>(slot) * p.n_kv + (c0 - p.n_q - p.n_kv);
         rope = false;
       }
-#pragma unroll 1
-      for (int j = 0; j < kHalf; j += 32) {
-        float lo[32], hi[32];
-        tmem_ld32f(taddr + h * kHeadDim + j, lo);
-        tmem_ld32f(taddr + h * kHeadDim + kHalf + j, hi);
+      float lo[32], hi[32];
+      tmem_ld32f(taddr + h * kHeadDim + j0, lo);
+      tmem_ld32f(taddr + h * kHeadDim + kHalf + j0, hi);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          lo[i] += __ldg(p.bias + c0 + j + i);
-          hi[i] += __ldg(p.bias + c0 + kHalf + j + i);
-        }
-        if (rope && row_ok) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float cs = __ldg(cosr + j + i), sn = __ldg(sinr + j + i);
-            const float a = lo[i], b = hi[i];
-            lo[i] = a * cs - b * sn;  // q*cos + rotate_half(q)*sin, first half:  q1*cos - q2*sin
-            hi[i] = b * cs + a * sn;  //                              second half: q2*cos + q1*sin
-          }
-        }
-        if (row_ok) {
-          store_row32_bf16(dst + j, lo, 32);
-          store_row32_bf16(dst + kHalf + j, hi, 32);
-        }
+      for (int i = 0; i < 32; ++i) {
+        const float a = lo[i] + __ldg(p.bias + c0 + j0 + i);
+        const float b = hi[i] + __ldg(p.bias + c0 + kHalf + j0 + i);
+        // q*cos + rotate_half(q)*sin:  first half q1*cos - q2*sin, second half q2*cos + q1*sin
+        lo[i] = rope ? a * cs[i] - b * sn[i] : a;
+        hi[i] = rope ? b * cs[i] + a * sn[i] : b;
+      }
+      if (row_ok) {
+        store_row32_bf16(dst + j0, lo, 32);
+        store_row32_bf16(dst + kHalf + j0, hi, 32);
       }
     }
   }
@@ -259,10 +263,10 @@ struct EpiSwiglu {
     __nv_bfloat16* act;  // [M, I]
     int ldo;             // = I
   };
-  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr) {
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
     const bool row_ok = row < d.M;
 #pragma unroll 1
-    for (int c = 0; c < 128; c += 32) {
+    for (int c = half * 64; c < half * 64 + 64; c += 32) {
       float g[32], u[32];
       tmem_ld32f(taddr + c, g);
       tmem_ld32f(taddr + 128 + c, u);
@@ -280,19 +284,19 @@ struct EpiSwiglu {
 // scale*acc, plus the scaled logit of the row's target column if it falls into this tile.
 struct EpiLse {
   struct Params {
-    float2* partial;    // [M, n_tiles] (max, sumexp)
+    float2* partial;    // [M, 2 * n_tiles] (max, sumexp) per half tile
     float* tgt_logit;   // [M]
     const int* target;  // [M]
     float scale;
   };
-  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr) {
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
     const bool row_ok = row < d.M;
     const int tgt = row_ok ? __ldg(p.target + row) : -1;
     constexpr float kLog2e = 1.4426950408889634f;
     float m_run = -INFINITY, s_run = 0.f, t_val = 0.f;
     bool t_hit = false;
 #pragma unroll 1
-    for (int c = 0; c < kBN; c += 32) {
+    for (int c = half * (kBN / 2); c < (half + 1) * (kBN / 2); c += 32) {
       float v[32];
       tmem_ld32f(taddr + c, v);
       const int col = n0 + c;
@@ -319,7 +323,7 @@ struct EpiLse {
       m_run = m_new;
     }
     if (row_ok) {
-      p.partial[static_cast<size_t>(row) * d.n_tiles + n_tile] = make_float2(m_run, s_run);
+      p.partial[static_cast<size_t>(row) * (2 * d.n_tiles) + 2 * n_tile + half] = make_float2(m_run, s_run);
       if (t_hit) p.tgt_logit[row] = t_val;
     }
   }
@@ -361,7 +365,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_tfull[i], 1);
-      mbar_init(&bar_tempty[i], 128 * kCtaGroup);
+      mbar_init(&bar_tempty[i], 256 * kCtaGroup);
     }
     fence_barrier_init();
   }
@@ -422,8 +426,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue (4 warps = 128 TMEM lanes = 128 rows)
-    const int ew = warp - 4;
+    // ===================================================== epilogue (2 warpgroups x 4 warps; 4 warps = 128 TMEM lanes = 128 rows)
+    const int ew = (warp - 4) & 3;       // TMEM lane quadrant (= warp % 4)
+    const int half = (warp - 4) >> 2;    // which half of the tile's columns / work items
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = worker; t < total_tiles; t += n_workers) {
@@ -433,7 +438,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBN);
-      Epi::run(ep, dims, row, n_tile * kBN, n_tile, taddr);
+      Epi::run(ep, dims, row, n_tile * kBN, n_tile, taddr, half);
       tc_fence_before();
       if (is_leader) mbar_arrive(&bar_tempty[acc]); else mbar_arrive_cluster(&bar_tempty[acc], 0);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -117,7 +117,7 @@ __global__ void mean_rows_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfl
 }
 
 // ------------------------------------------------------------------------------------------------ log-softmax reductions
-// Merge the per-tile (max, sumexp) partials of EpiLse: logp[r] = tgt_logit[r] - (m + log(sum)).
+// Merge the per-half-tile (max, sumexp) partials of EpiLse: logp[r] = tgt_logit[r] - (m + log(sum)).
 __global__ void lse_finalize_kernel(float* __restrict__ logp, const float2* __restrict__ partial, const float* __restrict__ tgt_logit,
                                     int R, int n_tiles) {
   const int warps_per_block = blockDim.x >> 5;
@@ -213,6 +213,14 @@ __global__ void repack_vocab_kernel(__nv_bfloat16* __restrict__ dst, const void*
     const int u = static_cast<int>(i / (static_cast<size_t>(mm) * n_clips));
     dst[(static_cast<size_t>(c) * n_v + u) * mm + d] = __float2bfloat16(load_as_f32(src, dtype, i));
   }
+}
+
+// dst[c][r] = src[r][c]   (rotary tables: [positions, head_dim/2] -> [head_dim/2, positions])
+__global__ void transpose_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, int rows, int cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i % cols;
+  dst[static_cast<size_t>(c) * rows + r] = src[i];
 }
 
 // ------------------------------------------------------------------------------------------------ dense score matrices
