@@ -236,6 +236,8 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attention_kernel(const AttnPa
     }
     if (active) {
       // ---- S = Q K^T  (16 rows x 64 keys per warp)
+      // short chunks (own segment of a caption, tail of the prefix): key blocks beyond nk are skipped (warp-uniform)
+      const int nb_lim = (nk + 15) >> 4 << 1;  // 8-key blocks to compute, rounded to the 16-key ldmatrix granularity
       float s[kAttnKeys / 8][4];
 #pragma unroll
       for (int i = 0; i < kAttnKeys / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attention_kernel(const AttnPa
       for (int kk = 0; kk < DH / 16; ++kk) {
 #pragma unroll
         for (int nb = 0; nb < kAttnKeys / 8; nb += 2) {
+          if (nb >= nb_lim) continue;
           const int key = nb * 8 + (lane & 7) + ((lane >> 4) << 3);
           const int col = kk * 16 + (((lane >> 3) & 1) << 3);
           uint32_t b0, b1, b2, b3;
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attention_kernel(const AttnPa
       // ---- O += P V
 #pragma unroll
       for (int kk = 0; kk < kAttnKeys / 16; ++kk) {
+        if (2 * kk >= nb_lim) continue;
         uint32_t pa[4];
         {
           __nv_bfloat162 t0 = __floats2bfloat162_rn(s[2 * kk][0], s[2 * kk][1]);

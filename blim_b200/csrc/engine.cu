@@ -27,6 +27,7 @@
 #include "attention.cuh"
 #include "gemm_sm100.cuh"
 #include "kernels_misc.cuh"
+#include "umma_probe.cuh"
 
 using namespace blim;
 typedef __nv_bfloat16 bf16;
@@ -1193,4 +1194,15 @@ extern "C" int blim_debug_gemm(blim_engine* e, int epilogue, const void* A, cons
   }
   e->gemm.cta_group = saved;
   return r;
+}
+
+extern "C" int blim_debug_umma(blim_engine* e, const void* A, const void* B, float* C, int K, int N, int b_mn_major, uint32_t lbo, uint32_t sbo,
+                               uint32_t kstep_bytes, void* stream) {
+  if (!e) return 1;
+  if (!A || !B || !C) return e->fail("bad debug_umma arguments");
+  CKE(cudaSetDevice(e->device));
+  cudaError_t r = launch_umma_probe(A, B, C, K, N, b_mn_major, lbo, sbo, kstep_bytes, S(stream));
+  if (r != cudaSuccess) return e->fail_cuda("umma probe", r);
+  e->launches++;
+  return 0;
 }

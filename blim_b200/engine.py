@@ -291,6 +291,17 @@ class Engine:
         self._check(self.lib.blim_profile_read(self.h, ctypes.byref(g), ctypes.byref(a), ctypes.byref(ng), ctypes.byref(na)))
         return dict(gemm_ms=g.value, attn_ms=a.value, gemm_launches=ng.value, attn_launches=na.value)
 
+    def debug_umma(self, A, B, b_mn_major, lbo=0, sbo=0, kstep=0):
+        """Single-CTA tcgen05 probe (see blim_debug_umma): A [128, K] bf16, B [N, K] or (b_mn_major) [K, N] bf16 -> fp32 [128, N]."""
+        with torch.cuda.device(self.device):
+            A, B = self._dev(A, torch.bfloat16), self._dev(B, torch.bfloat16)
+            K = A.shape[1]
+            N = B.shape[1] if b_mn_major else B.shape[0]
+            C = torch.zeros(128, N, dtype=torch.float32, device=self.device)
+            self._check(self.lib.blim_debug_umma(self.h, ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()),
+                                                 ctypes.c_void_p(C.data_ptr()), K, N, int(b_mn_major), lbo, sbo, kstep, self._stream()))
+        return C
+
     def debug_gemm(self, epilogue, A, W, bias=None, target=None, scale=1.0, cta_group=0, C=None):
         """Unit-test entry for the tcgen05 GEMM core (see blim_debug_gemm)."""
         with torch.cuda.device(self.device):

@@ -142,6 +142,12 @@ int blim_profile_read(blim_engine* e, double* gemm_ms, double* attn_ms, int64_t*
 int blim_debug_gemm(blim_engine* e, int epilogue, const void* A, const void* W, void* C, int M, int N, int K, const float* bias,
                     const int32_t* target, float scale, int cta_group, void* stream);
 
+/* Debug / unit-test entry: single-CTA tcgen05 probe C[128,N] = A[128,K] · B with thread-staged (manually swizzled)
+ * operands; B is [N][K] (K-major) or, with b_mn_major, [K][N] with explicit descriptor byte offsets.  Pins the
+ * shared-memory descriptor semantics the attention kernel relies on (tests/test_umma_probe_gpu.py). */
+int blim_debug_umma(blim_engine* e, const void* A, const void* B, float* C, int K, int N, int b_mn_major, uint32_t lbo, uint32_t sbo,
+                    uint32_t kstep_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
