@@ -1,0 +1,351 @@
+// tcgen05 / TMEM attention: varlen causal GQA with a shared (cascade) prefix segment -- the tensor-core version of
+// attention.cuh (same semantics, same AttnSeq description; reference: Qwen2SdpaAttention, modeling_qwen2_flash.py:685-709).
+//
+// One CTA = up to 128 stacked query rows (row = token * G + head-in-group of `128 / G` consecutive tokens of a
+// prefix-sharing group of sequences) x one KV head; one thread per row.
+//   S  = Q K^T      tcgen05.mma  M=128, N=16..64 (keys of the chunk), K=head_dim          -> TMEM columns [0, 64)
+//   softmax         each thread reads ITS row of S from TMEM (tcgen05.ld 32x32b): running max / sum / rescale are
+//                   thread-local, no shuffles; P (bf16) goes to a 128-byte-swizzled K-major tile in shared memory
+//   Oc = P V        tcgen05.mma  M=128, N=head_dim, K=keys; V stays [key][head_dim] in memory = MN-major B operand
+//                   (descriptor semantics pinned by tests/test_umma_probe_gpu.py)                -> TMEM columns [64, 64+head_dim)
+//   O  = O * corr + Oc   accumulated in registers (fp32), normalised and written as bf16 at the end.
+// Keys come in 64-key chunks: first the a_len prefix keys (all visible), then ONE contiguous range of own-run keys
+// [first token of the first sequence in the block, last token of the block]: key kt is visible to the query at token rt
+// iff seq_start(rt) <= kt <= rt and key_valid[kt] -- sequences are contiguous in the run, so "same sequence AND causal"
+// is an interval test.  K / V chunks are staged with cp.async (K for chunk c+1 while the softmax of chunk c runs, V for
+// c+1 while O is accumulated); two CTAs per SM overlap each other's phases.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "attention.cuh"
+#include "ptx_sm100.cuh"
+#include "umma_probe.cuh"
+
+namespace blim {
+
+struct AttnWorkTc {
+  int tok0;     // first token (run index) of the block
+  int n_tok;    // tokens in the block (<= 128 / G)
+  int a_start;  // prefix key rows [a_start, a_start + a_len) in k_a / v_a
+  int a_len;
+  int kb0;      // first own key row needed (= first token of the sequence that contains tok0)
+  int pad0, pad1, pad2;
+};
+struct AttnParamsTc {
+  const __nv_bfloat16* q;
+  __nv_bfloat16* o;
+  const __nv_bfloat16* k_a;
+  const __nv_bfloat16* v_a;
+  const __nv_bfloat16* k_b;
+  const __nv_bfloat16* v_b;
+  const uint8_t* key_valid;   // per own token, nullptr = all valid
+  const int* tok_seq_start;   // [T] first token of the sequence each token belongs to
+  const AttnWorkTc* works;
+  int n_q, n_kv, group;
+  float scale_log2;
+};
+
+constexpr int kTcKeys = 64;       // keys per chunk
+constexpr int kTcThreads = 128;
+constexpr int kTcTmemCols = 256;  // S (64) + Oc (<= 128), power of two
+
+template <int DH>
+constexpr int attn_tc_smem_bytes() {
+  // Q (DH/64 x 16 KB) + K chunk (DH/64 x 8 KB) + V chunk (DH/64 x 8 KB) + P (16 KB) + alignment slack
+  return (DH / 64) * 16384 + 2 * (DH / 64) * 8192 + 16384 + 1024;
+}
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int DH>
+__global__ void __launch_bounds__(kTcThreads, 2) attention_tc_kernel(const AttnParamsTc p) {
+  constexpr int kSub = DH / 64;  // 64-column sub-tiles along head_dim
+  extern __shared__ uint8_t smem_raw_tc[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* s_q = smem;                       // kSub x [128 rows x 128 B]
+  uint8_t* s_k = s_q + kSub * 16384;         // kSub x [64 keys x 128 B]   (K-major B of S = Q K^T)
+  uint8_t* s_v = s_k + kSub * 8192;          // kSub x [64 keys x 128 B]   (MN-major B of Oc = P V: sub-tile = 64 head_dim columns)
+  uint8_t* s_p = s_v + kSub * 8192;          // [128 rows x 64 keys]       (K-major A of Oc = P V)
+  __shared__ uint64_t bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+
+  const AttnWorkTc w = p.works[blockIdx.x];
+  const int kvh = blockIdx.y;
+  const int G = p.group;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (tid == 0) {
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<1>(&tmem_slot, kTcTmemCols);
+
+  // ---- this thread's row
+  const int tok_local = tid / G, head = tid - tok_local * G;
+  const bool row_ok = tok_local < w.n_tok;
+  const int rt = w.tok0 + (row_ok ? tok_local : 0);        // run token index of the row
+  const int seq_lo = row_ok ? __ldg(p.tok_seq_start + rt) : 0;
+  {
+    // Q row -> swizzled K-major tile (zero-filled for padding rows)
+    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH;
+#pragma unroll
+    for (int c = 0; c < DH / 8; ++c)
+      cp_async16(s_q + (c >> 3) * 16384 + sw128_offset(tid, (c & 7) * 8), src + c * 8, row_ok ? 16 : 0);
+    cp_async_commit();
+  }
+
+  const int n_a = (w.a_len + kTcKeys - 1) / kTcKeys;
+  const int own_len = w.tok0 + w.n_tok - w.kb0;            // own keys [kb0, tok0 + n_tok)
+  const int n_chunks = n_a + (own_len + kTcKeys - 1) / kTcKeys;
+
+  auto chunk_keys = [&](int c, int& nk, const __nv_bfloat16*& kb, const __nv_bfloat16*& vb, int& key0, bool& own) {
+    if (c < n_a) {
+      own = false;
+      key0 = c * kTcKeys;
+      nk = min(kTcKeys, w.a_len - key0);
+      const size_t off = static_cast<size_t>(w.a_start + key0) * p.n_kv + kvh * DH;
+      kb = p.k_a + off;
+      vb = p.v_a + off;
+    } else {
+      own = true;
+      key0 = w.kb0 + (c - n_a) * kTcKeys;                  // run token index of the chunk's first key
+      nk = min(kTcKeys, w.tok0 + w.n_tok - key0);
+      const size_t off = static_cast<size_t>(key0) * p.n_kv + kvh * DH;
+      kb = p.k_b + off;
+      vb = p.v_b + off;
+    }
+  };
+  // stage one [64 keys x DH] matrix: row r of the chunk -> kSub swizzled sub-tiles; rows >= nk are zero-filled
+  auto stage = [&](uint8_t* dst, const __nv_bfloat16* src, int nk) {
+#pragma unroll
+    for (int it = 0; it < kTcKeys * (DH / 8) / kTcThreads; ++it) {
+      const int idx = tid + it * kTcThreads;
+      const int r = idx / (DH / 8), c = idx % (DH / 8);
+      const bool ok = r < nk;
+      cp_async16(dst + (c >> 3) * 8192 + sw128_offset(r, (c & 7) * 8), src + (ok ? static_cast<size_t>(r) * p.n_kv + c * 8 : 0), ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+
+  if (n_chunks > 0) {
+    int nk, key0; bool own;
+    const __nv_bfloat16 *kb, *vb;
+    chunk_keys(0, nk, kb, vb, key0, own);
+    stage(s_k, kb, nk);
+    stage(s_v, vb, nk);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);   // this thread's TMEM lane
+  const uint32_t t_s = t_row, t_o = t_row + 64;
+
+  float o[DH];
+#pragma unroll
+  for (int i = 0; i < DH; ++i) o[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  for (int c = 0; c < n_chunks; ++c) {
+    int nk, key0; bool own;
+    const __nv_bfloat16 *kb_cur, *vb_cur;
+    chunk_keys(c, nk, kb_cur, vb_cur, key0, own);
+    const int nk16 = (nk + 15) & ~15;
+    const uint32_t ph = static_cast<uint32_t>(c & 1);
+
+    // ---- K(c) (and, for c == 0, Q) have landed -> S = Q K^T
+    cp_async_wait<1>();
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16_ex(128, nk16, 0);
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        const uint64_t da = make_smem_desc_sw128(smem_u32(s_q) + (kk >> 2) * 16384 + (kk & 3) * 32);
+        const uint64_t db = make_smem_desc_sw128(smem_u32(s_k) + (kk >> 2) * 8192 + (kk & 3) * 32);
+        umma_bf16<1>(tmem, da, db, idesc, kk != 0 ? 1u : 0u);
+      }
+      umma_commit(&bar_s);
+    }
+    mbar_wait(&bar_s, ph);
+    tc_fence_after();
+
+    // ---- softmax of this row over the chunk's keys; P -> smem
+    float corr;
+    {
+      float sv[kTcKeys];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h * 32 < nk16) {   // warp-uniform
+          float t[32];
+          tmem_ld32_nowait(t_s + h * 32, t);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[h * 32 + i] = t[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[h * 32 + i] = 0.f;
+        }
+      }
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kTcKeys; ++j) {
+        bool vis = row_ok && j < nk;
+        if (own) {
+          const int kt = key0 + j;
+          vis = vis && kt >= seq_lo && kt <= rt;
+          if (vis && p.key_valid) vis = p.key_valid[kt] != 0;
+        }
+        const float val = vis ? sv[j] * p.scale_log2 : -INFINITY;
+        sv[j] = val;
+        cmax = fmaxf(cmax, val);
+      }
+      const float m_new = fmaxf(m_run, cmax);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      corr = exp2f(m_run - m_use);
+      m_run = m_new;
+      float csum = 0.f;
+#pragma unroll
+      for (int j8 = 0; j8 < kTcKeys / 8; ++j8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = exp2f(sv[j8 * 8 + 2 * e] - m_use), p1 = exp2f(sv[j8 * 8 + 2 * e + 1] - m_use);
+          csum += p0 + p1;
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+          pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        if (j8 * 8 < nk16) *reinterpret_cast<uint4*>(s_p + sw128_offset(tid, j8 * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      l_run = l_run * corr + csum;
+    }
+
+    // ---- V(c) has landed, P is written -> Oc = P V
+    cp_async_wait<0>();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16_ex(128, DH, 1);
+      for (int kk = 0; kk < nk16 / 16; ++kk) {
+        const uint64_t da = make_smem_desc_sw128(smem_u32(s_p) + kk * 32);
+        const uint64_t db = make_smem_desc_raw(smem_u32(s_v) + kk * 2048, 8192, 1024);
+        umma_bf16<1>(tmem + 64, da, db, idesc, kk != 0 ? 1u : 0u);
+      }
+      umma_commit(&bar_o);
+    }
+    // K buffer is free (S = Q K^T of this chunk completed): prefetch K(c+1) under the P V product
+    int nk_n = 0, key0_n; bool own_n;
+    const __nv_bfloat16 *kb_n = nullptr, *vb_n = nullptr;
+    if (c + 1 < n_chunks) {
+      chunk_keys(c + 1, nk_n, kb_n, vb_n, key0_n, own_n);
+      stage(s_k, kb_n, nk_n);
+    }
+    mbar_wait(&bar_o, ph);
+    tc_fence_after();
+#pragma unroll
+    for (int h = 0; h < DH / 32; ++h) {
+      float t[32];
+      tmem_ld32_nowait(t_o + h * 32, t);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[h * 32 + i] = o[h * 32 + i] * corr + t[i];
+    }
+    tc_fence_before();
+    // V and P buffers are free (Oc = P V completed): prefetch V(c+1) under the next S = Q K^T
+    if (c + 1 < n_chunks) stage(s_v, vb_n, nk_n);
+  }
+
+  // ---- normalise and write this row
+  if (row_ok) {
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    __nv_bfloat16* dst = p.o + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH;
+#pragma unroll
+    for (int c8 = 0; c8 < DH / 8; ++c8) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(o[c8 * 8 + 2 * e] * inv, o[c8 * 8 + 2 * e + 1] * inv);
+        pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      *reinterpret_cast<uint4*>(dst + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+  cp_async_wait<0>();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc<1>(tmem, kTcTmemCols);
+}
+
+// Host: blocks of 128 / G consecutive tokens over every prefix-sharing group of consecutive sequences, plus the
+// per-token "first token of my sequence" table.
+inline void build_attn_works_tc(const AttnSeq* seqs, int n_seqs, int group, std::vector<AttnWorkTc>& works, std::vector<int>& tok_seq_start,
+                                int n_tokens) {
+  works.clear();
+  tok_seq_start.assign(n_tokens, 0);
+  const int tpb = 128 / group;
+  int s0 = 0;
+  while (s0 < n_seqs) {
+    int s1 = s0 + 1;
+    if (seqs[s0].a_len > 0)
+      while (s1 < n_seqs && seqs[s1].a_len == seqs[s0].a_len && seqs[s1].a_start == seqs[s0].a_start &&
+             seqs[s1].q_start == seqs[s1 - 1].q_start + seqs[s1 - 1].q_len)
+        ++s1;
+    for (int s = s0; s < s1; ++s)
+      for (int t = 0; t < seqs[s].q_len; ++t) tok_seq_start[seqs[s].q_start + t] = seqs[s].q_start;
+    const int g0 = seqs[s0].q_start, g1 = seqs[s1 - 1].q_start + seqs[s1 - 1].q_len;
+    int cur = s0;
+    for (int t0 = g0; t0 < g1; t0 += tpb) {
+      while (seqs[cur].q_start + seqs[cur].q_len <= t0) ++cur;
+      AttnWorkTc w;
+      w.tok0 = t0;
+      w.n_tok = (g1 - t0 < tpb) ? g1 - t0 : tpb;
+      w.a_start = seqs[s0].a_start;
+      w.a_len = seqs[s0].a_len;
+      w.kb0 = seqs[cur].q_start;
+      w.pad0 = w.pad1 = w.pad2 = 0;
+      works.push_back(w);
+    }
+    s0 = s1;
+  }
+}
+
+inline cudaError_t launch_attention_tc(const AttnParamsTc& p, int n_works, int n_kv_heads, int head_dim, cudaStream_t stream) {
+  if (n_works <= 0) return cudaSuccess;
+  dim3 grid(static_cast<unsigned>(n_works), static_cast<unsigned>(n_kv_heads));
+  if (head_dim == 128) {
+    static bool set = false;
+    if (!set) {
+      cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc_smem_bytes<128>());
+      if (e != cudaSuccess) return e;
+      set = true;
+    }
+    attention_tc_kernel<128><<<grid, kTcThreads, attn_tc_smem_bytes<128>(), stream>>>(p);
+  } else if (head_dim == 64) {
+    static bool set = false;
+    if (!set) {
+      cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc_smem_bytes<64>());
+      if (e != cudaSuccess) return e;
+      set = true;
+    }
+    attention_tc_kernel<64><<<grid, kTcThreads, attn_tc_smem_bytes<64>(), stream>>>(p);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace blim

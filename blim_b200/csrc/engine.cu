@@ -25,6 +25,7 @@
 
 #include "../../include/blim_b200.h"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "gemm_sm100.cuh"
 #include "kernels_misc.cuh"
 #include "umma_probe.cuh"
@@ -138,7 +139,8 @@ struct blim_engine {
 
   // workspaces
   DevBuf x, xn, q, attn, k_own, v_own, act, kp, vp, prefix_last, vis, proj_tmp, lm_a, pred, partial, tgt_logit, logp, uniq_scores;
-  DevBuf d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map;
+  DevBuf d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
+  bool attn_tc = true;  // tcgen05 attention (BLIM_ATTN=mma selects the mma.sync kernel)
   size_t partial_tiles = 0;
 
   // optional per-launch device timing (bench.py roofline): CUDA events around every GEMM / attention launch
@@ -224,7 +226,7 @@ extern "C" void blim_destroy(blim_engine* e) {
   DevBuf* bufs[] = {&e->embed, &e->lm_head, &e->visual_head, &e->norm, &e->rope_cos, &e->rope_sin, &e->feats, &e->vocab, &e->tvg_vis,
                     &e->x, &e->xn, &e->q, &e->attn, &e->k_own, &e->v_own, &e->act, &e->kp, &e->vp, &e->prefix_last, &e->vis,
                     &e->proj_tmp, &e->lm_a, &e->pred, &e->partial, &e->tgt_logit, &e->logp, &e->uniq_scores, &e->d_tok_src,
-                    &e->d_tok_pos, &e->d_key_valid, &e->d_seqs, &e->d_works, &e->d_idx, &e->d_targets, &e->d_row_off, &e->d_map};
+                    &e->d_tok_pos, &e->d_key_valid, &e->d_seqs, &e->d_works, &e->d_idx, &e->d_targets, &e->d_row_off, &e->d_map, &e->d_seq_start};
   for (DevBuf* b : bufs) b->release();
   for (LayerW& l : e->layers) {
     l.w_qkv.release(); l.w_o.release(); l.w_gu.release(); l.w_down.release(); l.b_qkv.release(); l.ln1.release(); l.ln2.release();
@@ -262,6 +264,10 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
   e->Pmax = cfg->max_prefix_tokens > 0 ? cfg->max_prefix_tokens : 32768;
   e->Umax = std::min(e->Pmax, 8192);
   e->gemm.num_sms = prop.multiProcessorCount;
+  {
+    const char* a = getenv("BLIM_ATTN");
+    e->attn_tc = !(a && std::string(a) == "mma");
+  }
   e->gemm.cta_group = cfg->gemm_cta_group == 1 ? 1 : 2;  // default: CTA pairs (cta_group::2)
   auto bad = [&](const char* m) {
     g_create_error = m;
@@ -284,8 +290,8 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
       {&e->prefix_last, static_cast<size_t>(e->Umax) * e->H * 4}, {&e->vis, P * e->H * 2}, {&e->proj_tmp, T * e->H * 2},
       {&e->lm_a, T * e->H * 2}, {&e->pred, T * e->MM * 2}, {&e->tgt_logit, T * 4}, {&e->logp, T * 4},
       {&e->d_tok_src, T * 4}, {&e->d_tok_pos, T * 4}, {&e->d_key_valid, T}, {&e->d_seqs, T * sizeof(AttnSeq)},
-      {&e->d_works, (T * e->G / kAttnRows + T + 1) * sizeof(AttnWork)}, {&e->d_idx, T * 4}, {&e->d_targets, T * 4},
-      {&e->d_row_off, (T + 1) * 4}};
+      {&e->d_works, (T * e->G / kAttnRows + T + 1) * sizeof(AttnWorkTc)}, {&e->d_idx, T * 4}, {&e->d_targets, T * 4},
+      {&e->d_row_off, (T + 1) * 4}, {&e->d_seq_start, T * 4}};
   for (auto& a : allocs) {
     cudaError_t r = a.b->reserve(a.bytes);
     if (r != cudaSuccess) {
@@ -538,10 +544,21 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
   for (int p : run.tok_pos)
     if (p < 0 || p >= e->rope_n) return e->fail("sequence longer than the rotary table (max_positions)");
   std::vector<AttnWork> works;
-  build_attn_works(run.seqs.data(), static_cast<int>(run.seqs.size()), e->G, works);
+  std::vector<AttnWorkTc> works_tc;
+  std::vector<int> seq_start;
+  int n_works;
+  if (e->attn_tc) {
+    build_attn_works_tc(run.seqs.data(), static_cast<int>(run.seqs.size()), e->G, works_tc, seq_start, T);
+    n_works = static_cast<int>(works_tc.size());
+    CKR(upload(e, e->d_works, works_tc.data(), works_tc.size() * sizeof(AttnWorkTc), st));
+    CKR(upload(e, e->d_seq_start, seq_start.data(), T * sizeof(int), st));
+  } else {
+    build_attn_works(run.seqs.data(), static_cast<int>(run.seqs.size()), e->G, works);
+    n_works = static_cast<int>(works.size());
+    CKR(upload(e, e->d_works, works.data(), works.size() * sizeof(AttnWork), st));
+    CKR(upload(e, e->d_seqs, run.seqs.data(), run.seqs.size() * sizeof(AttnSeq), st));
+  }
   CKR(upload(e, e->d_tok_pos, run.tok_pos.data(), T * sizeof(int), st));
-  CKR(upload(e, e->d_seqs, run.seqs.data(), run.seqs.size() * sizeof(AttnSeq), st));
-  CKR(upload(e, e->d_works, works.data(), works.size() * sizeof(AttnWork), st));
   if (run.any_invalid) CKR(upload(e, e->d_key_valid, run.key_valid.data(), T, st));
   if (!assembled) {
     CKR(upload(e, e->d_tok_src, run.tok_src.data(), T * sizeof(int), st));
@@ -557,15 +574,26 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
     bf16* v_out = to_prefix_cache ? vpl : e->v_own.as<bf16>();
     CKR(rmsnorm(e, e->xn.as<bf16>(), e->x.as<float>(), nullptr, nullptr, w.ln1.as<float>(), T, st));
     CKR(gemm_qkv(e, e->xn.as<bf16>(), w, T, e->q.as<bf16>(), k_out, v_out, e->d_tok_pos.as<int>(), st));
-    AttnParams ap;
-    ap.q = e->q.as<bf16>(); ap.o = e->attn.as<bf16>();
-    ap.k_a = kpl; ap.v_a = vpl; ap.k_b = k_out; ap.v_b = v_out;
-    ap.key_valid = run.any_invalid ? e->d_key_valid.as<uint8_t>() : nullptr;
-    ap.seqs = e->d_seqs.as<AttnSeq>(); ap.works = e->d_works.as<AttnWork>();
-    ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G;
-    ap.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(e->DH));
+    const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(e->DH));
+    cudaError_t r;
     e->tic(1, st);
-    cudaError_t r = launch_attention(ap, static_cast<int>(works.size()), e->NKV, e->DH, st);
+    if (e->attn_tc) {
+      AttnParamsTc ap;
+      ap.q = e->q.as<bf16>(); ap.o = e->attn.as<bf16>();
+      ap.k_a = kpl; ap.v_a = vpl; ap.k_b = k_out; ap.v_b = v_out;
+      ap.key_valid = run.any_invalid ? e->d_key_valid.as<uint8_t>() : nullptr;
+      ap.tok_seq_start = e->d_seq_start.as<int>(); ap.works = e->d_works.as<AttnWorkTc>();
+      ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G; ap.scale_log2 = scale_log2;
+      r = launch_attention_tc(ap, n_works, e->NKV, e->DH, st);
+    } else {
+      AttnParams ap;
+      ap.q = e->q.as<bf16>(); ap.o = e->attn.as<bf16>();
+      ap.k_a = kpl; ap.v_a = vpl; ap.k_b = k_out; ap.v_b = v_out;
+      ap.key_valid = run.any_invalid ? e->d_key_valid.as<uint8_t>() : nullptr;
+      ap.seqs = e->d_seqs.as<AttnSeq>(); ap.works = e->d_works.as<AttnWork>();
+      ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G; ap.scale_log2 = scale_log2;
+      r = launch_attention(ap, n_works, e->NKV, e->DH, st);
+    }
     e->toc(st);
     if (r != cudaSuccess) return e->fail_cuda("attention launch", r);
     e->launches++;
