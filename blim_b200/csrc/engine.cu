@@ -648,7 +648,18 @@ static int plan_batches(blim_engine* e, const std::vector<UnitPlan>& units, cons
                         std::vector<std::vector<BatchUnit>>& batches) {
   batches.clear();
   std::vector<BatchUnit> cur;
-  const int pcap = std::min(e->Pmax, e->Tmax);  // a prefix run is also one decoder run
+  const int pcap_hard = std::min(e->Pmax, e->Tmax);  // a prefix run is also one decoder run
+  // balance: n batches of roughly equal size instead of (n-1) full ones and a small tail (small runs waste the GEMMs)
+  long long tot_p = 0, tot_s = 0, tot_i = 0;
+  int max_p = 0, max_s = 0;
+  for (const UnitPlan& up : units) {
+    tot_p += up.prefix_len;
+    max_p = std::max(max_p, up.prefix_len);
+    for (int it : up.items) { tot_s += items[it].suf_len; max_s = std::max(max_s, items[it].suf_len); ++tot_i; }
+  }
+  long long nb = std::max<long long>(1, std::max((tot_p + pcap_hard - 1) / pcap_hard, std::max((tot_s + e->Tmax - 1) / e->Tmax, (tot_i + max_items - 1) / max_items)));
+  const int pcap = static_cast<int>(std::min<long long>(pcap_hard, (tot_p + nb - 1) / nb + max_p));
+  const int scap = static_cast<int>(std::min<long long>(e->Tmax, (tot_s + nb - 1) / nb + max_s));
   long long cp = 0, cs = 0;
   int ci = 0;
   auto flush = [&]() {
@@ -662,10 +673,10 @@ static int plan_batches(blim_engine* e, const std::vector<UnitPlan>& units, cons
     while (pos < up.items.size()) {
       const int first_len = items[up.items[pos]].suf_len;
       if (first_len > e->Tmax) return e->fail("a suffix sequence exceeds max_run_tokens");
-      if (cp + up.prefix_len > pcap || static_cast<int>(cur.size()) + 1 > e->Umax || cs + first_len > e->Tmax || ci + 1 > max_items) flush();
+      if (cp + up.prefix_len > pcap || static_cast<int>(cur.size()) + 1 > e->Umax || cs + first_len > scap || ci + 1 > max_items) flush();
       BatchUnit bu{static_cast<int>(u), static_cast<int>(pos), static_cast<int>(pos)};
       cp += up.prefix_len;
-      while (pos < up.items.size() && cs + items[up.items[pos]].suf_len <= e->Tmax && ci + 1 <= max_items) {
+      while (pos < up.items.size() && cs + items[up.items[pos]].suf_len <= scap && ci + 1 <= max_items) {
         cs += items[up.items[pos]].suf_len;
         ++ci; ++pos;
       }
