@@ -12,8 +12,9 @@
 // Keys come in 64-key chunks: first the a_len prefix keys (all visible), then ONE contiguous range of own-run keys
 // [first token of the first sequence in the block, last token of the block]: key kt is visible to the query at token rt
 // iff seq_start(rt) <= kt <= rt and key_valid[kt] -- sequences are contiguous in the run, so "same sequence AND causal"
-// is an interval test.  K / V chunks are staged with cp.async (K for chunk c+1 while the softmax of chunk c runs, V for
-// c+1 while O is accumulated); two CTAs per SM overlap each other's phases.
+// is an interval test.  K / V chunks are staged by TMA (64 keys x 64 columns boxes, SWIZZLE_128B, mbarrier completion):
+// K for chunk c+1 is in flight while the softmax of chunk c runs, V for c+1 while O is accumulated; two CTAs per SM
+// overlap each other's phases.  Rows of a box beyond the chunk's keys hold other (finite) cache rows and meet P = 0.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -22,6 +23,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "gemm_sm100.cuh"
 #include "ptx_sm100.cuh"
 #include "umma_probe.cuh"
 
@@ -38,10 +40,8 @@ struct AttnWorkTc {
 struct AttnParamsTc {
   const __nv_bfloat16* q;
   __nv_bfloat16* o;
-  const __nv_bfloat16* k_a;
-  const __nv_bfloat16* v_a;
-  const __nv_bfloat16* k_b;
-  const __nv_bfloat16* v_b;
+  int a_row0;                 // row offset of this layer inside the tensor map of the prefix K / V buffers
+  int b_row0;                 // row offset inside the tensor map of the own-run K / V buffers
   const uint8_t* key_valid;   // per own token, nullptr = all valid
   const int* tok_seq_start;   // [T] first token of the sequence each token belongs to
   const AttnWorkTc* works;
@@ -68,15 +68,18 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32])
 }
 
 template <int DH>
-__global__ void __launch_bounds__(kTcThreads, 2) attention_tc_kernel(const AttnParamsTc p) {
+__global__ void __launch_bounds__(kTcThreads, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_constant__ CUtensorMap tm_va,
+                    const __grid_constant__ CUtensorMap tm_kb, const __grid_constant__ CUtensorMap tm_vb, const AttnParamsTc p) {
   constexpr int kSub = DH / 64;  // 64-column sub-tiles along head_dim
+  constexpr uint32_t kChunkBytes = kSub * 8192;
   extern __shared__ uint8_t smem_raw_tc[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* s_q = smem;                       // kSub x [128 rows x 128 B]
   uint8_t* s_k = s_q + kSub * 16384;         // kSub x [64 keys x 128 B]   (K-major B of S = Q K^T)
   uint8_t* s_v = s_k + kSub * 8192;          // kSub x [64 keys x 128 B]   (MN-major B of Oc = P V: sub-tile = 64 head_dim columns)
   uint8_t* s_p = s_v + kSub * 8192;          // [128 rows x 64 keys]       (K-major A of Oc = P V)
-  __shared__ uint64_t bar_s, bar_o;
+  __shared__ uint64_t bar_s, bar_o, bar_k, bar_v;
   __shared__ uint32_t tmem_slot;
 
   const AttnWorkTc w = p.works[blockIdx.x];
@@ -87,7 +90,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) attention_tc_kernel(const AttnP
   if (tid == 0) {
     mbar_init(&bar_s, 1);
     mbar_init(&bar_o, 1);
+    mbar_init(&bar_k, 1);
+    mbar_init(&bar_v, 1);
     fence_barrier_init();
+    tma_prefetch_desc(&tm_ka);
+    tma_prefetch_desc(&tm_va);
+    tma_prefetch_desc(&tm_kb);
+    tma_prefetch_desc(&tm_vb);
   }
   if (warp == 0) tmem_alloc<1>(&tmem_slot, kTcTmemCols);
 
@@ -109,46 +118,36 @@ __global__ void __launch_bounds__(kTcThreads, 2) attention_tc_kernel(const AttnP
   const int own_len = w.tok0 + w.n_tok - w.kb0;            // own keys [kb0, tok0 + n_tok)
   const int n_chunks = n_a + (own_len + kTcKeys - 1) / kTcKeys;
 
-  auto chunk_keys = [&](int c, int& nk, const __nv_bfloat16*& kb, const __nv_bfloat16*& vb, int& key0, bool& own) {
+  // chunk c -> key count, first key (segment A: index inside the prefix; own: run token index), tensor-map row
+  auto chunk_keys = [&](int c, int& nk, int& key0, bool& own, int& tm_row) {
     if (c < n_a) {
       own = false;
       key0 = c * kTcKeys;
       nk = min(kTcKeys, w.a_len - key0);
-      const size_t off = static_cast<size_t>(w.a_start + key0) * p.n_kv + kvh * DH;
-      kb = p.k_a + off;
-      vb = p.v_a + off;
+      tm_row = p.a_row0 + w.a_start + key0;
     } else {
       own = true;
-      key0 = w.kb0 + (c - n_a) * kTcKeys;                  // run token index of the chunk's first key
+      key0 = w.kb0 + (c - n_a) * kTcKeys;
       nk = min(kTcKeys, w.tok0 + w.n_tok - key0);
-      const size_t off = static_cast<size_t>(key0) * p.n_kv + kvh * DH;
-      kb = p.k_b + off;
-      vb = p.v_b + off;
+      tm_row = p.b_row0 + key0;
     }
   };
-  // stage one [64 keys x DH] matrix: row r of the chunk -> kSub swizzled sub-tiles; rows >= nk are zero-filled
-  auto stage = [&](uint8_t* dst, const __nv_bfloat16* src, int nk) {
+  // one elected thread: TMA a [64 keys x DH] chunk as kSub boxes of 64 columns
+  auto stage = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tm_row) {
+    mbar_arrive_expect_tx(bar, kChunkBytes);
 #pragma unroll
-    for (int it = 0; it < kTcKeys * (DH / 8) / kTcThreads; ++it) {
-      const int idx = tid + it * kTcThreads;
-      const int r = idx / (DH / 8), c = idx % (DH / 8);
-      const bool ok = r < nk;
-      cp_async16(dst + (c >> 3) * 8192 + sw128_offset(r, (c & 7) * 8), src + (ok ? static_cast<size_t>(r) * p.n_kv + c * 8 : 0), ok ? 16 : 0);
-    }
-    cp_async_commit();
+    for (int sub = 0; sub < kSub; ++sub) tma_load_2d(dst + sub * 8192, tm, bar, kvh * DH + sub * 64, tm_row);
   };
-
-  if (n_chunks > 0) {
-    int nk, key0; bool own;
-    const __nv_bfloat16 *kb, *vb;
-    chunk_keys(0, nk, kb, vb, key0, own);
-    stage(s_k, kb, nk);
-    stage(s_v, vb, nk);
-  }
 
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();   // barriers initialised, TMEM allocated
   tc_fence_after();
+  if (tid == 0) {
+    int nk, key0, row; bool own;
+    chunk_keys(0, nk, key0, own, row);
+    stage(s_k, own ? &tm_kb : &tm_ka, &bar_k, row);
+    stage(s_v, own ? &tm_vb : &tm_va, &bar_v, row);
+  }
   const uint32_t tmem = tmem_slot;
   const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);   // this thread's TMEM lane
   const uint32_t t_s = t_row, t_o = t_row + 64;
@@ -156,20 +155,20 @@ __global__ void __launch_bounds__(kTcThreads, 2) attention_tc_kernel(const AttnP
   float o[DH];
 #pragma unroll
   for (int i = 0; i < DH; ++i) o[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;   // running max in scaled (log2) units
+  cp_async_wait<0>();                      // this thread's Q row has landed
 
   for (int c = 0; c < n_chunks; ++c) {
-    int nk, key0; bool own;
-    const __nv_bfloat16 *kb_cur, *vb_cur;
-    chunk_keys(c, nk, kb_cur, vb_cur, key0, own);
+    int nk, key0, tm_row_unused; bool own;
+    chunk_keys(c, nk, key0, own, tm_row_unused);
     const int nk16 = (nk + 15) & ~15;
     const uint32_t ph = static_cast<uint32_t>(c & 1);
 
-    // ---- K(c) (and, for c == 0, Q) have landed -> S = Q K^T
-    cp_async_wait<1>();
+    // ---- K(c) has landed (and, for c == 0, every thread's Q row) -> S = Q K^T
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
+      mbar_wait(&bar_k, ph);
       tc_fence_after();
       const uint32_t idesc = make_idesc_bf16_ex(128, nk16, 0);
 #pragma unroll
@@ -182,37 +181,44 @@ __global__ void __launch_bounds__(kTcThreads, 2) attention_tc_kernel(const AttnP
     }
     mbar_wait(&bar_s, ph);
     tc_fence_after();
+    // the K buffer is free again: K(c+1) streams in under the softmax and the P V product
+    int nk_n = 0, key0_n = 0, row_n = 0; bool own_n = false;
+    if (c + 1 < n_chunks) chunk_keys(c + 1, nk_n, key0_n, own_n, row_n);
+    if (tid == 0 && c + 1 < n_chunks) stage(s_k, own_n ? &tm_kb : &tm_ka, &bar_k, row_n);
 
     // ---- softmax of this row over the chunk's keys; P -> smem
     float corr;
     {
       float sv[kTcKeys];
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_s, r0);
+        if (nk16 > 32) tmem_ld32(t_s + 32, r1);   // warp-uniform
+        tmem_ld_wait();
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (h * 32 < nk16) {   // warp-uniform
-          float t[32];
-          tmem_ld32_nowait(t_s + h * 32, t);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sv[h * 32 + i] = t[i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sv[h * 32 + i] = 0.f;
+        for (int i = 0; i < 32; ++i) {
+          sv[i] = __uint_as_float(r0[i]);
+          sv[32 + i] = nk16 > 32 ? __uint_as_float(r1[i]) : 0.f;
         }
       }
+      // visible keys of this row inside the chunk form an interval [j_lo, j_hi]
+      int j_lo = 0, j_hi = nk - 1;
+      if (own) {
+        j_lo = max(0, seq_lo - key0);
+        j_hi = min(nk - 1, rt - key0);
+      }
+      const unsigned span = j_hi >= j_lo ? static_cast<unsigned>(j_hi - j_lo) : 0u;
+      const bool any = j_hi >= j_lo;
       float cmax = -INFINITY;
 #pragma unroll
       for (int j = 0; j < kTcKeys; ++j) {
-        bool vis = row_ok && j < nk;
-        if (own) {
-          const int kt = key0 + j;
-          vis = vis && kt >= seq_lo && kt <= rt;
-          if (vis && p.key_valid) vis = p.key_valid[kt] != 0;
-        }
-        const float val = vis ? sv[j] * p.scale_log2 : -INFINITY;
+        bool vis = any && static_cast<unsigned>(j - j_lo) <= span;
+        if (own && p.key_valid && vis) vis = p.key_valid[key0 + j] != 0;
+        const float val = vis ? sv[j] : -INFINITY;
         sv[j] = val;
         cmax = fmaxf(cmax, val);
       }
-      const float m_new = fmaxf(m_run, cmax);
+      const float m_new = fmaxf(m_run, cmax * p.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       corr = exp2f(m_run - m_use);
       m_run = m_new;
@@ -222,7 +228,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) attention_tc_kernel(const AttnP
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p0 = exp2f(sv[j8 * 8 + 2 * e] - m_use), p1 = exp2f(sv[j8 * 8 + 2 * e + 1] - m_use);
+          const float p0 = exp2f(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
+          const float p1 = exp2f(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
           csum += p0 + p1;
           __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
           pk[e] = *reinterpret_cast<uint32_t*>(&b2);
@@ -232,12 +239,12 @@ __global__ void __launch_bounds__(kTcThreads, 2) attention_tc_kernel(const AttnP
       l_run = l_run * corr + csum;
     }
 
-    // ---- V(c) has landed, P is written -> Oc = P V
-    cp_async_wait<0>();
+    // ---- P is written (generic proxy -> async proxy), V(c) has landed -> Oc = P V
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
+      mbar_wait(&bar_v, ph);
       tc_fence_after();
       const uint32_t idesc = make_idesc_bf16_ex(128, DH, 1);
       for (int kk = 0; kk < nk16 / 16; ++kk) {
@@ -247,25 +254,18 @@ __global__ void __launch_bounds__(kTcThreads, 2) attention_tc_kernel(const AttnP
       }
       umma_commit(&bar_o);
     }
-    // K buffer is free (S = Q K^T of this chunk completed): prefetch K(c+1) under the P V product
-    int nk_n = 0, key0_n; bool own_n;
-    const __nv_bfloat16 *kb_n = nullptr, *vb_n = nullptr;
-    if (c + 1 < n_chunks) {
-      chunk_keys(c + 1, nk_n, kb_n, vb_n, key0_n, own_n);
-      stage(s_k, kb_n, nk_n);
-    }
     mbar_wait(&bar_o, ph);
     tc_fence_after();
+    // V and P buffers are free: V(c+1) streams in under the accumulation and the next S = Q K^T
+    if (tid == 0 && c + 1 < n_chunks) stage(s_v, own_n ? &tm_vb : &tm_va, &bar_v, row_n);
 #pragma unroll
     for (int h = 0; h < DH / 32; ++h) {
       float t[32];
       tmem_ld32_nowait(t_o + h * 32, t);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[h * 32 + i] = o[h * 32 + i] * corr + t[i];
+      for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], corr, t[i]);
     }
     tc_fence_before();
-    // V and P buffers are free (Oc = P V completed): prefetch V(c+1) under the next S = Q K^T
-    if (c + 1 < n_chunks) stage(s_v, vb_n, nk_n);
   }
 
   // ---- normalise and write this row
@@ -283,7 +283,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) attention_tc_kernel(const AttnP
       *reinterpret_cast<uint4*>(dst + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
-  cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -323,7 +322,17 @@ inline void build_attn_works_tc(const AttnSeq* seqs, int n_seqs, int group, std:
   }
 }
 
-inline cudaError_t launch_attention_tc(const AttnParamsTc& p, int n_works, int n_kv_heads, int head_dim, cudaStream_t stream) {
+// bf16 [rows, n_kv] K / V buffer -> tensor map with 64-column x 64-row boxes (SWIZZLE_128B)
+inline bool make_kv_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t n_kv) {
+  return make_tmap_bf16(out, base, rows, n_kv, n_kv, kTcKeys);
+}
+
+struct AttnTcMaps {
+  CUtensorMap ka, va, kb, vb;
+};
+
+inline cudaError_t launch_attention_tc(const AttnTcMaps& m, const AttnParamsTc& p, int n_works, int n_kv_heads, int head_dim,
+                                       cudaStream_t stream) {
   if (n_works <= 0) return cudaSuccess;
   dim3 grid(static_cast<unsigned>(n_works), static_cast<unsigned>(n_kv_heads));
   if (head_dim == 128) {
@@ -333,7 +342,7 @@ inline cudaError_t launch_attention_tc(const AttnParamsTc& p, int n_works, int n
       if (e != cudaSuccess) return e;
       set = true;
     }
-    attention_tc_kernel<128><<<grid, kTcThreads, attn_tc_smem_bytes<128>(), stream>>>(p);
+    attention_tc_kernel<128><<<grid, kTcThreads, attn_tc_smem_bytes<128>(), stream>>>(m.ka, m.va, m.kb, m.vb, p);
   } else if (head_dim == 64) {
     static bool set = false;
     if (!set) {
@@ -341,7 +350,7 @@ inline cudaError_t launch_attention_tc(const AttnParamsTc& p, int n_works, int n
       if (e != cudaSuccess) return e;
       set = true;
     }
-    attention_tc_kernel<64><<<grid, kTcThreads, attn_tc_smem_bytes<64>(), stream>>>(p);
+    attention_tc_kernel<64><<<grid, kTcThreads, attn_tc_smem_bytes<64>(), stream>>>(m.ka, m.va, m.kb, m.vb, p);
   } else {
     return cudaErrorInvalidValue;
   }

@@ -141,6 +141,7 @@ struct blim_engine {
   DevBuf x, xn, q, attn, k_own, v_own, act, kp, vp, prefix_last, vis, proj_tmp, lm_a, pred, partial, tgt_logit, logp, uniq_scores;
   DevBuf d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
   bool attn_tc = true;  // tcgen05 attention (BLIM_ATTN=mma selects the mma.sync kernel)
+  CUtensorMap tm_kp, tm_vp, tm_kown, tm_vown;  // K / V buffers as TMA tensors (tcgen05 attention)
   size_t partial_tiles = 0;
 
   // optional per-launch device timing (bench.py roofline): CUDA events around every GEMM / attention launch
@@ -299,6 +300,15 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
       blim_destroy(e);
       return 1;
     }
+  }
+  // K / V buffers are read in whole 64-row TMA boxes: rows outside a chunk must hold finite values
+  cudaMemset(e->kp.p, 0, e->kp.cap); cudaMemset(e->vp.p, 0, e->vp.cap);
+  cudaMemset(e->k_own.p, 0, e->k_own.cap); cudaMemset(e->v_own.p, 0, e->v_own.cap);
+  if (!make_kv_tmap(&e->tm_kp, e->kp.p, static_cast<uint64_t>(e->NL) * P, e->NKVD) || !make_kv_tmap(&e->tm_vp, e->vp.p, static_cast<uint64_t>(e->NL) * P, e->NKVD) ||
+      !make_kv_tmap(&e->tm_kown, e->k_own.p, T, e->NKVD) || !make_kv_tmap(&e->tm_vown, e->v_own.p, T, e->NKVD)) {
+    g_create_error = "cuTensorMapEncodeTiled failed for the K/V buffers";
+    blim_destroy(e);
+    return 1;
   }
   *out = e;
   return 0;
@@ -580,11 +590,16 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
     if (e->attn_tc) {
       AttnParamsTc ap;
       ap.q = e->q.as<bf16>(); ap.o = e->attn.as<bf16>();
-      ap.k_a = kpl; ap.v_a = vpl; ap.k_b = k_out; ap.v_b = v_out;
+      ap.a_row0 = l * e->Pmax;
+      ap.b_row0 = to_prefix_cache ? l * e->Pmax : 0;
+      AttnTcMaps maps;
+      maps.ka = e->tm_kp; maps.va = e->tm_vp;
+      maps.kb = to_prefix_cache ? e->tm_kp : e->tm_kown;
+      maps.vb = to_prefix_cache ? e->tm_vp : e->tm_vown;
       ap.key_valid = run.any_invalid ? e->d_key_valid.as<uint8_t>() : nullptr;
       ap.tok_seq_start = e->d_seq_start.as<int>(); ap.works = e->d_works.as<AttnWorkTc>();
       ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G; ap.scale_log2 = scale_log2;
-      r = launch_attention_tc(ap, n_works, e->NKV, e->DH, st);
+      r = launch_attention_tc(maps, ap, n_works, e->NKV, e->DH, st);
     } else {
       AttnParams ap;
       ap.q = e->q.as<bf16>(); ap.o = e->attn.as<bf16>();
