@@ -546,7 +546,11 @@ static int project(blim_engine* e, const bf16* feats, int rows, int which, bf16*
 }
 
 // Run the decoder over a flat token list.  x must already hold the input embeddings when `assembled` is true.
-static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool assembled, cudaStream_t st) {
+// `last_rows` (prefix runs): the only tokens whose final state is needed.  In the last layer everything after the
+// attention is then computed for those rows only and their final residual-stream rows land in e->prefix_last[0..U);
+// an empty list means the run only has to fill the KV cache (the last layer stops after its QKV projection).
+static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool assembled, cudaStream_t st,
+                       const std::vector<int>* last_rows = nullptr) {
   const int T = run.T();
   if (T == 0) return 0;
   if (T > e->Tmax) return e->fail("internal: run exceeds max_run_tokens");
@@ -584,6 +588,8 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
     bf16* v_out = to_prefix_cache ? vpl : e->v_own.as<bf16>();
     CKR(rmsnorm(e, e->xn.as<bf16>(), e->x.as<float>(), nullptr, nullptr, w.ln1.as<float>(), T, st));
     CKR(gemm_qkv(e, e->xn.as<bf16>(), w, T, e->q.as<bf16>(), k_out, v_out, e->d_tok_pos.as<int>(), st));
+    const bool prune = last_rows != nullptr && l == e->NL - 1;
+    if (prune && last_rows->empty()) break;
     const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(e->DH));
     cudaError_t r;
     e->tic(1, st);
@@ -612,6 +618,23 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
     e->toc(st);
     if (r != cudaSuccess) return e->fail_cuda("attention launch", r);
     e->launches++;
+    if (prune) {
+      // last layer of a prefix run: o_proj + MLP only for the rows whose final state is read
+      const int U = static_cast<int>(last_rows->size());
+      if (U > e->Umax) return e->fail("internal: too many prefix units in one run");
+      CKR(upload(e, e->d_idx, last_rows->data(), U * sizeof(int), st));
+      gather_rows_bf16_kernel<<<U, 128, 0, st>>>(e->xn.as<bf16>(), e->attn.as<bf16>(), e->d_idx.as<int>(), U, e->NQ);
+      CKL();
+      gather_rows_f32_kernel<<<U, 256, 0, st>>>(e->prefix_last.as<float>(), e->x.as<float>(), e->d_idx.as<int>(), U, e->H);
+      CKL();
+      EpiResid::Params pl{e->prefix_last.as<float>(), e->H};
+      CKR(gemm<EpiResid>(e, e->xn.as<bf16>(), e->NQ, w.w_o.as<bf16>(), e->NQ, U, e->H, e->NQ, pl, st));
+      CKR(rmsnorm(e, e->xn.as<bf16>(), e->prefix_last.as<float>(), nullptr, nullptr, w.ln2.as<float>(), U, st));
+      EpiSwiglu::Params psl{e->act.as<bf16>(), e->I};
+      CKR(gemm<EpiSwiglu>(e, e->xn.as<bf16>(), e->H, w.w_gu.as<bf16>(), e->H, U, 2 * e->I, e->H, psl, st));
+      CKR(gemm<EpiResid>(e, e->act.as<bf16>(), e->I, w.w_down.as<bf16>(), e->I, U, e->H, e->I, pl, st));
+      break;
+    }
     EpiResid::Params pr{e->x.as<float>(), e->H};
     CKR(gemm<EpiResid>(e, e->attn.as<bf16>(), e->NQ, w.w_o.as<bf16>(), e->NQ, T, e->H, e->NQ, pr, st));
     CKR(rmsnorm(e, e->xn.as<bf16>(), e->x.as<float>(), nullptr, nullptr, w.ln2.as<float>(), T, st));
@@ -631,15 +654,6 @@ static int lse_rows(blim_engine* e, const bf16* A, int lda, const bf16* W, int l
   EpiLse::Params p{e->partial.as<float2>(), e->tgt_logit.as<float>(), targets_dev, scale};
   CKR(gemm<EpiLse>(e, A, lda, W, ldw, R, N, K, p, st));
   lse_finalize_kernel<<<(R + 7) / 8, 256, 0, st>>>(logp_dev, e->partial.as<float2>(), e->tgt_logit.as<float>(), R, 2 * n_tiles);
-  CKL();
-  return 0;
-}
-
-static int save_prefix_last(blim_engine* e, const std::vector<int>& last_tok, cudaStream_t st) {
-  const int U = static_cast<int>(last_tok.size());
-  if (U == 0) return 0;
-  CKR(upload(e, e->d_idx, last_tok.data(), U * sizeof(int), st));
-  gather_rows_f32_kernel<<<U, 256, 0, st>>>(e->prefix_last.as<float>(), e->x.as<float>(), e->d_idx.as<int>(), U, e->H);
   CKL();
   return 0;
 }
@@ -794,8 +808,7 @@ static int score_vtg(blim_engine* e, bool prior, const std::vector<std::pair<int
       unit_len[b] = run.T() - unit_start[b];
       last_tok[b] = run.T() - 1;
     }
-    CKR(run_decoder(e, run, true, false, st));
-    CKR(save_prefix_last(e, last_tok, st));
+    CKR(run_decoder(e, run, true, false, st, &last_tok));
     // ---- suffix run
     run.clear();
     std::vector<int> row_idx, targets, row_off, item_keys;
@@ -923,28 +936,50 @@ static int score_tvg(blim_engine* e, bool prior, const std::vector<std::pair<int
       any_prefix = any_prefix || plen > 0;
     }
     if (any_prefix) {
-      CKR(run_decoder(e, run, true, false, st));
-      if (!prior) CKR(save_prefix_last(e, last_tok, st));
+      const std::vector<int> none;
+      CKR(run_decoder(e, run, true, false, st, prior ? &none : &last_tok));
     }
     // ---- suffix run.  Visual rows come straight from the pooled tvg_mlp table: tok_src = -1 - row, with e->vis
     //      temporarily replaced by the table (assemble reads `visual` rows by index).
     run.clear();
-    std::vector<int> item_keys, item_q0, item_unit_b;
+    std::vector<int> item_keys, item_q0, item_unit_b, item_row0;
     for (size_t b = 0; b < batch.size(); ++b) {
       const UnitPlan& up = units[batch[b].unit];
+      // TVG prior: the state of the last text token (position T0-1, CPN-masked as a key) only depends on the visible
+      // header, T0 and the token id, not on the video: one 1-token sequence per distinct (T0, token) of this unit
+      std::map<std::pair<int, int>, int> lt_tok;
+      if (prior) {
+        for (int ii = batch[b].item_begin; ii < batch[b].item_end; ++ii) {
+          const int t = keys[items[up.items[ii]].key].second;
+          const int T0 = tt.img_pos[t];
+          if ((T0 - 1) < e->tvg_prefix_len) continue;  // visible as a key: stays inside the item's own sequence
+          const std::pair<int, int> k(T0, tt.ids[tt.off[t] + T0 - 1]);
+          if (lt_tok.count(k)) continue;
+          lt_tok[k] = run.begin_seq(unit_start[b], unit_len[b]);
+          run.push(k.second, T0 - 1, false);
+          run.end_seq();
+        }
+      }
       for (int ii = batch[b].item_begin; ii < batch[b].item_end; ++ii) {
         const Item& it = items[up.items[ii]];
         const int v = keys[it.key].first, t = keys[it.key].second;
         const int T0 = tt.img_pos[t];
-        const int q0 = run.begin_seq(unit_start[b], unit_len[b]);
+        int q0 = run.begin_seq(unit_start[b], unit_len[b]);
+        int row0 = -1;
         if (prior) {
-          // last text token: a query at position T0-1; as a key it is CPN-masked unless it lies inside the visible header
-          run.push(tt.ids[tt.off[t] + T0 - 1], T0 - 1, (T0 - 1) < e->tvg_prefix_len);
+          if ((T0 - 1) < e->tvg_prefix_len) {
+            row0 = q0;
+            run.push(tt.ids[tt.off[t] + T0 - 1], T0 - 1, true);
+            q0 += 1;
+          } else {
+            row0 = lt_tok[std::pair<int, int>(T0, tt.ids[tt.off[t] + T0 - 1])];
+          }
         }
         for (int c = 0; c < NC - 1; ++c) run.push(-1 - (v * NC + c), T0 + c);
         run.end_seq();
         item_keys.push_back(it.key);
-        item_q0.push_back(q0);
+        item_q0.push_back(q0);       // first pooled visual row of the item
+        item_row0.push_back(row0);   // prior: token whose state predicts clip 0
         item_unit_b.push_back(static_cast<int>(b));
       }
     }
@@ -967,7 +1002,7 @@ static int score_tvg(blim_engine* e, bool prior, const std::vector<std::pair<int
         for (int c = 0; c < NC; ++c) {
           int src;
           if (!prior) src = (c == 0) ? -1 - item_unit_b[i] : item_q0[i] + (c - 1);
-          else src = item_q0[i] + c;
+          else src = (c == 0) ? item_row0[i] : item_q0[i] + (c - 1);
           row_idx[static_cast<size_t>(c) * P + p] = src;
         }
         targets[p] = e->video_labels[keys[item_keys[i]].first];
@@ -1009,40 +1044,44 @@ extern "C" int blim_score_pairs(blim_engine* e, int kind, const int32_t* pair_v,
   if (tt.n == 0) return e->fail(is_tvg ? "TVG texts not set" : "VTG texts not set");
   if (e->n_videos == 0) return e->fail("videos not set");
   if (!is_tvg && !prior && (!e->proj[0].w0.p)) return e->fail("mm_projector.mlp weights not loaded");
-  // ---- unique keys
-  //   VTG: (v,t)   VTG prior: (t) [all videos share n_clips]   TVG: (v,t)   TVG prior: (header group, T0, v)
-  std::map<std::vector<int64_t>, int> key_of;
-  std::vector<std::pair<int, int>> keys;
-  std::vector<int> map(n_pairs);
-  auto make_key = [&](int v, int t) {
-    std::vector<int64_t> k;
-    if (kind == BLIM_VTG || kind == BLIM_TVG) k = {v, t};
-    else if (kind == BLIM_VTG_PRIOR) k = {t};
-    else {
-      // texts with the same visible header, the same length T0 and the same last text token give the same prior
-      const int T0 = tt.img_pos[t];
-      const int plen = std::min(e->tvg_prefix_len, T0 - 1);
-      k = {v, T0, tt.ids[tt.off[t] + T0 - 1]};
-      for (int j = 0; j < plen; ++j) k.push_back(tt.ids[tt.off[t] + j]);
+  // ---- unique keys (packed into 64 bits, sort + unique)
+  //   VTG: (v,t)   VTG prior: (t) [all videos share n_clips]   TVG: (v,t)
+  //   TVG prior: (visible-header group, T0, last text token, v): texts with the same visible header, the same length and
+  //   the same last text token give the same prior for a video
+  std::vector<int> hdr_group;  // TVG prior: header group of every text
+  if (kind == BLIM_TVG_PRIOR) {
+    std::map<std::vector<int32_t>, int> groups;
+    hdr_group.resize(tt.n);
+    for (int t = 0; t < tt.n; ++t) {
+      const int plen = std::min(e->tvg_prefix_len, tt.img_pos[t] - 1);
+      std::vector<int32_t> h(tt.ids.begin() + tt.off[t], tt.ids.begin() + tt.off[t] + plen);
+      auto it = groups.find(h);
+      if (it == groups.end()) it = groups.emplace(h, static_cast<int>(groups.size())).first;
+      hdr_group[t] = it->second;
     }
-    return k;
+    if (groups.size() > 1024) return e->fail("too many distinct TVG prompt headers");
+  }
+  auto make_key = [&](int v, int t) -> uint64_t {
+    if (kind == BLIM_VTG || kind == BLIM_TVG) return (static_cast<uint64_t>(v) << 32) | static_cast<uint32_t>(t);
+    if (kind == BLIM_VTG_PRIOR) return static_cast<uint32_t>(t);
+    const uint64_t T0 = static_cast<uint64_t>(tt.img_pos[t]) & 0x3FFF;              // < 2^14: positions are bounded by the rotary table
+    const uint64_t tok = static_cast<uint64_t>(tt.ids[tt.off[t] + tt.img_pos[t] - 1]);  // < 2^20 checked below
+    return (static_cast<uint64_t>(hdr_group[t]) << 54) | (T0 << 40) | (tok << 20) | static_cast<uint64_t>(v);
   };
+  if (kind == BLIM_TVG_PRIOR && (e->V > (1 << 20) || e->n_videos > (1 << 20) || e->rope_n > (1 << 14))) return e->fail("TVG prior key does not fit 64 bits");
+  std::vector<std::pair<uint64_t, int>> tagged(n_pairs);
   for (int64_t i = 0; i < n_pairs; ++i) {
     const int v = pair_v[i], t = pair_t[i];
     if (v < 0 || v >= e->n_videos || t < 0 || t >= tt.n) return e->fail("pair index out of range");
-    key_of.emplace(make_key(v, t), static_cast<int>(i));  // remembers the first pair carrying this key
+    tagged[i] = std::make_pair(make_key(v, t), static_cast<int>(i));
   }
-  {
-    // key indices in sorted key order: VTG work is grouped by video, TVG work by (video, text)
-    int idx = 0;
-    keys.reserve(key_of.size());
-    for (auto& kv : key_of) {
-      const int first = kv.second;
-      keys.emplace_back(pair_v[first], pair_t[first]);
-      kv.second = idx++;
-    }
+  std::sort(tagged.begin(), tagged.end());
+  std::vector<std::pair<int, int>> keys;   // representative (v, t) of every unique key, in sorted key order
+  std::vector<int> map(n_pairs);
+  for (int64_t i = 0; i < n_pairs; ++i) {
+    if (i == 0 || tagged[i].first != tagged[i - 1].first) keys.emplace_back(pair_v[tagged[i].second], pair_t[tagged[i].second]);
+    map[tagged[i].second] = static_cast<int>(keys.size()) - 1;
   }
-  for (int64_t i = 0; i < n_pairs; ++i) map[i] = key_of.find(make_key(pair_v[i], pair_t[i]))->second;
   CKE(e->uniq_scores.reserve(keys.size() * 4));
   if (is_tvg) CKR(score_tvg(e, prior, keys, e->uniq_scores.as<float>(), st));
   else CKR(score_vtg(e, prior, keys, e->uniq_scores.as<float>(), st));

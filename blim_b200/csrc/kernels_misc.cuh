@@ -101,6 +101,16 @@ __global__ void gather_rows_f32_kernel(float* __restrict__ dst, const float* __r
   for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) *reinterpret_cast<float4*>(d + c) = *reinterpret_cast<const float4*>(s + c);
 }
 
+// dst[r] = src[idx[r]] for bf16 rows of `w` elements (w % 8 == 0)
+__global__ void gather_rows_bf16_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ src, const int* __restrict__ idx,
+                                        int R, int w) {
+  const int r = blockIdx.x;
+  if (r >= R) return;
+  const __nv_bfloat16* s = src + static_cast<size_t>(idx[r]) * w;
+  __nv_bfloat16* d = dst + static_cast<size_t>(r) * w;
+  for (int c = threadIdx.x * 8; c < w; c += blockDim.x * 8) *reinterpret_cast<uint4*>(d + c) = *reinterpret_cast<const uint4*>(s + c);
+}
+
 // TVG visual rows: mean over the `group` tokens of a clip (reference: frame_feature.mean(1), modeling_videochat_flash.py:243),
 // fp32 accumulate, bf16 result.  in [R*group, H] -> out [R, H]
 __global__ void mean_rows_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ in, int R, int group, int H) {

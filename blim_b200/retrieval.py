@@ -98,22 +98,10 @@ def _world():
     return 0, 1
 
 
-def _all_gather_var(t, world):
-    """All-gather of a 1-D tensor whose length differs per rank (pad to the maximum, one collective per call)."""
-    n = torch.tensor([t.numel()], device=t.device, dtype=torch.long)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    sizes = [int(s.item()) for s in sizes]
-    width = max(sizes)
-    buf = torch.zeros(width, device=t.device, dtype=t.dtype)
-    buf[:t.numel()] = t
-    out = torch.empty(world * width, device=t.device, dtype=t.dtype)
-    dist.all_gather_into_tensor(out, buf)
-    return torch.cat([out[r * width:r * width + sizes[r]] for r in range(world)])
-
-
 class PairPlan:
-    """Candidate pairs of one evaluation: per direction the top-k index arrays, plus the deduplicated union."""
+    """Candidate pairs of one evaluation: per direction the top-k index arrays, plus the deduplicated union.
+    Device tensors for the kernels and numpy copies for the host-side scheduler (one D2H at construction, so nothing
+    later has to synchronise the stream to look at indices)."""
 
     def __init__(self, v2t_iv2, t2v_iv2, topk, device):
         self.v2t_idx = v2t_iv2.to(device).topk(k=min(v2t_iv2.shape[1], topk), dim=1).indices  # [Nv, k] text ids
@@ -133,12 +121,18 @@ class PairPlan:
         self.t2v_in_union = inverse[v_a.numel():]
         self.union_v = torch.div(self.union_key, nt, rounding_mode="floor")
         self.union_t = self.union_key - self.union_v * nt
+        packed = torch.cat([self.union_v, self.union_t, v_a, t_a, v_b, t_b]).cpu().numpy().astype(np.int32)
+        nu, na, nb = self.union_v.numel(), v_a.numel(), v_b.numel()
+        self.union_np = (packed[:nu], packed[nu:2 * nu])
+        self.v2t_np = (packed[2 * nu:2 * nu + na], packed[2 * nu + na:2 * nu + 2 * na])
+        self.t2v_np = (packed[2 * nu + 2 * na:2 * nu + 2 * na + nb], packed[2 * nu + 2 * na + nb:])
 
 
 def score_all(model, plan: PairPlan, cpn=True, full=True, distributed=False):
     """Scores every term evaluation() needs on the deduplicated pair set.  Multi-GPU: the pairs are sharded by the id
-    that owns the shared prefix (each video / text prefix is prefilled on exactly one rank), one all-gather per score
-    kind of compact fp32 scores.
+    that owns the shared prefix (each video / text prefix is prefilled on exactly one rank); every rank derives all
+    ranks' shards from the same plan, so the only communication is ONE all-gather of padded fp32 scores per score kind
+    (no index or size exchange, no host synchronisation).
     Returns a dict of compact device tensors aligned with plan.union_* (vtg, tvg) / plan.v2t_pairs (vtg_prior) /
     plan.t2v_pairs (tvg_prior)."""
     m = _engine_model(model)
@@ -147,25 +141,30 @@ def score_all(model, plan: PairPlan, cpn=True, full=True, distributed=False):
 
     def run(kind, pv, pt):
         if world == 1:
-            return eng.score_pairs(kind, pv.cpu().numpy(), pt.cpu().numpy())
+            return eng.score_pairs(kind, pv, pt)
         # shard by the id that owns the shared prefix: video for VTG / TVG prior, text for VTG prior / TVG
         owner = pv if kind in (VTG, TVG_PRIOR) else pt
-        mine = (owner % world) == rank
-        sel = mine.nonzero().flatten()
-        local = eng.score_pairs(kind, pv[sel].cpu().numpy(), pt[sel].cpu().numpy())
-        all_scores = _all_gather_var(local, world)
-        all_sel = _all_gather_var(sel, world)
-        out = torch.empty(pv.numel(), dtype=torch.float32, device=eng.device)
-        out[all_sel] = all_scores
+        shards = [np.nonzero(owner % world == r)[0] for r in range(world)]
+        width = max(len(x) for x in shards)
+        buf = torch.zeros(width, dtype=torch.float32, device=eng.device)
+        mine = shards[rank]
+        if len(mine):
+            eng.score_pairs(kind, pv[mine], pt[mine], out=buf[:len(mine)])
+        gathered = torch.empty(world * width, dtype=torch.float32, device=eng.device)
+        dist.all_gather_into_tensor(gathered, buf)
+        src = np.concatenate([r * width + np.arange(len(x)) for r, x in enumerate(shards)])
+        dst = np.concatenate(shards)
+        out = torch.empty(len(pv), dtype=torch.float32, device=eng.device)
+        out[torch.from_numpy(dst).to(eng.device, non_blocking=True)] = gathered[torch.from_numpy(src).to(eng.device, non_blocking=True)]
         return out
 
-    out = {"vtg": run(VTG, plan.union_v, plan.union_t)}
+    out = {"vtg": run(VTG, *plan.union_np)}
     if cpn:
-        out["vtg_prior"] = run(VTG_PRIOR, *plan.v2t_pairs)
+        out["vtg_prior"] = run(VTG_PRIOR, *plan.v2t_np)
     if full:
-        out["tvg"] = run(TVG, plan.union_v, plan.union_t)
+        out["tvg"] = run(TVG, *plan.union_np)
         if cpn:
-            out["tvg_prior"] = run(TVG_PRIOR, *plan.t2v_pairs)
+            out["tvg_prior"] = run(TVG_PRIOR, *plan.t2v_np)
     return out
 
 

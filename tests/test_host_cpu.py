@@ -63,8 +63,12 @@ def test_pair_plan_union_and_inverse():
 class _FakeEngine:
     device = torch.device("cpu")
 
-    def score_pairs(self, kind, pv, pt):
-        return torch.from_numpy((kind * 1000 + np.asarray(pv) * 7 + np.asarray(pt) * 0.25).astype(np.float32))
+    def score_pairs(self, kind, pv, pt, out=None):
+        res = torch.from_numpy((kind * 1000 + np.asarray(pv) * 7 + np.asarray(pt) * 0.25).astype(np.float32))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
 
 
 class _FakeModel:
