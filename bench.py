@@ -111,43 +111,49 @@ def measured_peaks():
 
 
 def algorithmic_flops(cfg, corpus, plan, cpn=True, full=True):
-    """FLOPs the algorithm needs (non-padding tokens, every shared prefix once, logits only at scored
-    positions).  Returns (gemm_flops, attention_flops)."""
+    """FLOPs the algorithm needs -- non-padding tokens, every shared prefix once, logits only at scored
+    positions, and in the last layer of a prefix only the QKV projection (KV cache) for all tokens plus the rest of the
+    layer for the one token whose state is read.  Returns (gemm_flops, attention_flops)."""
     H, I, V, MM, L = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size, cfg.mm_hidden_size, cfg.num_layers
     nkv = cfg.num_kv_heads * cfg.head_dim
-    p_dec = 2.0 * L * (H * (H + 2 * nkv) + H * H + 3 * H * I)
+    p_qkv = 2.0 * H * (H + 2 * nkv)                      # per token, one layer
+    p_layer = p_qkv + 2.0 * (H * H + 3 * H * I)          # per token, one layer
+    p_dec = L * p_layer
     p_lm = 2.0 * H * V
+    prefix = lambda n_tok, n_last: n_tok * ((L - 1) * p_layer + p_qkv) + n_last * (p_layer - p_qkv)
     att = lambda q, c: 4.0 * L * cfg.num_heads * cfg.head_dim * q * c
     n_vis = corpus.n_clips * cfg.tokens_per_clip
     nc = corpus.n_clips
-    uv, ut = plan.union_v.cpu().numpy(), plan.union_t.cpu().numpy()
+    uv, ut = plan.union_np
     cap = np.array([int((lab != -100).sum()) for lab in corpus.vtg_labels])             # scored tokens per text (caption + 2)
     pre = np.array([int((lab == -100).sum()) - 1 for lab in corpus.vtg_labels])          # prompt tokens without the image sentinel
     t0 = np.array([int((ids == -200).nonzero()[0]) for ids in corpus.tvg_ids])           # TVG text length
+    last_tok = np.array([int(ids[int((ids == -200).nonzero()[0]) - 1]) for ids in corpus.tvg_ids])
     g = a = 0.0
     vids = np.unique(uv)
     s_v = pre[0] + n_vis
-    g += len(vids) * (s_v * p_dec + n_vis * 2.0 * (MM * H + H * H))                       # video prefixes + projector
+    g += len(vids) * (prefix(s_v, 1) + n_vis * 2.0 * (MM * H + H * H))                    # video prefixes + projector
     a += len(vids) * att(s_v, (s_v + 1) / 2)
     suf = cap[ut] - 1                                                                     # decoder tokens per pair
     g += float(suf.sum()) * (p_dec + p_lm) + len(vids) * p_lm
     a += float(sum(att(q, s_v + (q + 1) / 2) for q in suf))
     if cpn:
-        texts = np.unique(plan.v2t_pairs[1].cpu().numpy())
+        texts = np.unique(plan.v2t_np[1])
         q = cap[texts] - 1
-        g += pre[0] * p_dec + float(q.sum()) * (p_dec + p_lm) + p_lm
+        g += prefix(pre[0], 1) + float(q.sum()) * (p_dec + p_lm) + p_lm
         a += float(sum(att(x, pre[0] + (x + 1) / 2) for x in q))
     if full:
         texts = np.unique(ut)
         head = nc * (2.0 * H * MM + 2.0 * MM * corpus.n)
-        g += float(t0[texts].sum()) * p_dec + len(uv) * ((nc - 1) * p_dec + head)
+        g += float(sum(prefix(x, 1) for x in t0[texts])) + len(uv) * ((nc - 1) * p_dec + head)
         g += len(vids) * n_vis * 2.0 * (MM * H + H * H)                                   # tvg_mlp projector
         a += float(sum(att(x, (x + 1) / 2) for x in t0[texts])) + float(sum(att(nc - 1, t0[t] + nc / 2) for t in ut))
         if cpn:
-            pv, pt = plan.t2v_pairs[0].cpu().numpy(), plan.t2v_pairs[1].cpu().numpy()
-            uniq = len(set(zip(pv.tolist(), t0[pt].tolist())))
-            g += corpus.tvg_prefix_length * p_dec + uniq * (nc * p_dec + head)
-            a += uniq * att(nc, corpus.tvg_prefix_length + nc / 2)
+            pv, pt = plan.t2v_np
+            uniq = len(set(zip(pv.tolist(), t0[pt].tolist(), last_tok[pt].tolist())))
+            uniq_lt = len(set(zip(t0[pt].tolist(), last_tok[pt].tolist())))
+            g += prefix(corpus.tvg_prefix_length, 0) + (uniq * (nc - 1) + uniq_lt) * p_dec + uniq * head
+            a += uniq * att(nc - 1, corpus.tvg_prefix_length + nc / 2) + uniq_lt * att(1, corpus.tvg_prefix_length)
     return g, a
 
 

@@ -289,6 +289,279 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_cons
   if (warp == 0) tmem_dealloc<1>(tmem, kTcTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------ v2: O stays in TMEM
+// Same decomposition, deeper overlap (the production kernel; the one above is kept for A/B runs, BLIM_ATTN=tc1):
+//   * 256 threads: two threads per query row (warps w and w+4 share a TMEM lane quadrant); each handles 32 of the chunk's
+//     64 keys and half of the head_dim columns, the row maximum is exchanged through shared memory;
+//   * O is accumulated by the tensor core in TMEM (Oc = P V with accumulate); it is only touched by threads when the
+//     running reference maximum has to grow by more than 2^8 ("lazy rescale": tcgen05.ld -> scale -> tcgen05.st), so the
+//     per-chunk register traffic of the first kernel (128 TMEM->register FMAs per row) disappears;
+//   * S = Q K^T of chunk c+1 is issued right behind Oc = P V of chunk c, so it runs under the softmax of nobody and is
+//     ready when the threads come back; V is double-buffered, K single-buffered, both by TMA.
+constexpr int kTc2Threads = 256;
+
+template <int DH>
+constexpr int attn_tc2_smem_bytes() {
+  // Q (DH/64 x 16 KB) + K chunk (DH/64 x 8 KB) + 2 x V chunk (DH/64 x 8 KB) + P (16 KB) + alignment slack
+  return (DH / 64) * 16384 + 3 * (DH / 64) * 8192 + 16384 + 1024;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(kTc2Threads, 2)
+attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_constant__ CUtensorMap tm_va,
+                     const __grid_constant__ CUtensorMap tm_kb, const __grid_constant__ CUtensorMap tm_vb, const AttnParamsTc p) {
+  constexpr int kSub = DH / 64;
+  constexpr uint32_t kChunkBytes = kSub * 8192;
+  constexpr float kGrow = 8.0f;  // lazy rescale threshold (log2 units): P stays below 2^8
+  extern __shared__ uint8_t smem_raw_tc[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* s_q = smem;
+  uint8_t* s_k = s_q + kSub * 16384;
+  uint8_t* s_v = s_k + kSub * 8192;          // two stages
+  uint8_t* s_p = s_v + 2 * kSub * 8192;
+  __shared__ uint64_t bar_s, bar_o, bar_k, bar_v[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_x[2][128];              // per-row exchange between the two threads of a row (max, then sum)
+
+  const AttnWorkTc w = p.works[blockIdx.x];
+  const int kvh = blockIdx.y;
+  const int G = p.group;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid & 127, half = tid >> 7;
+
+  if (tid == 0) {
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_o, 1);
+    mbar_init(&bar_k, 1);
+    mbar_init(&bar_v[0], 1);
+    mbar_init(&bar_v[1], 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_ka);
+    tma_prefetch_desc(&tm_va);
+    tma_prefetch_desc(&tm_kb);
+    tma_prefetch_desc(&tm_vb);
+  }
+  if (warp == 0) tmem_alloc<1>(&tmem_slot, kTcTmemCols);
+
+  const int tok_local = r / G, head = r - tok_local * G;
+  const bool row_ok = tok_local < w.n_tok;
+  const int rt = w.tok0 + (row_ok ? tok_local : 0);
+  const int seq_lo = row_ok ? __ldg(p.tok_seq_start + rt) : 0;
+  {
+    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH;
+#pragma unroll
+    for (int cc = 0; cc < DH / 16; ++cc) {
+      const int c = half * (DH / 16) + cc;
+      cp_async16(s_q + (c >> 3) * 16384 + sw128_offset(r, (c & 7) * 8), src + c * 8, row_ok ? 16 : 0);
+    }
+    cp_async_commit();
+  }
+
+  const int n_a = (w.a_len + kTcKeys - 1) / kTcKeys;
+  const int own_len = w.tok0 + w.n_tok - w.kb0;
+  const int n_chunks = n_a + (own_len + kTcKeys - 1) / kTcKeys;
+
+  auto chunk_keys = [&](int c, int& nk, int& key0, bool& own, int& tm_row) {
+    if (c < n_a) {
+      own = false;
+      key0 = c * kTcKeys;
+      nk = min(kTcKeys, w.a_len - key0);
+      tm_row = p.a_row0 + w.a_start + key0;
+    } else {
+      own = true;
+      key0 = w.kb0 + (c - n_a) * kTcKeys;
+      nk = min(kTcKeys, w.tok0 + w.n_tok - key0);
+      tm_row = p.b_row0 + key0;
+    }
+  };
+  auto stage = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tm_row) {
+    mbar_arrive_expect_tx(bar, kChunkBytes);
+#pragma unroll
+    for (int sub = 0; sub < kSub; ++sub) tma_load_2d(dst + sub * 8192, tm, bar, kvh * DH + sub * 64, tm_row);
+  };
+  auto stage_k = [&](int c) {
+    int nk, key0, row; bool own;
+    chunk_keys(c, nk, key0, own, row);
+    stage(s_k, own ? &tm_kb : &tm_ka, &bar_k, row);
+  };
+  auto stage_v = [&](int c) {
+    int nk, key0, row; bool own;
+    chunk_keys(c, nk, key0, own, row);
+    stage(s_v + (c & 1) * kSub * 8192, own ? &tm_vb : &tm_va, &bar_v[c & 1], row);
+  };
+  auto issue_s = [&](int c, uint32_t tmem) {   // S = Q K^T of chunk c (tid 0 only)
+    int nk, key0, row; bool own;
+    chunk_keys(c, nk, key0, own, row);
+    const int nk16 = (nk + 15) & ~15;
+    mbar_wait(&bar_k, static_cast<uint32_t>(c & 1));
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16_ex(128, nk16, 0);
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+      const uint64_t da = make_smem_desc_sw128(smem_u32(s_q) + (kk >> 2) * 16384 + (kk & 3) * 32);
+      const uint64_t db = make_smem_desc_sw128(smem_u32(s_k) + (kk >> 2) * 8192 + (kk & 3) * 32);
+      umma_bf16<1>(tmem, da, db, idesc, kk != 0 ? 1u : 0u);
+    }
+    umma_commit(&bar_s);
+  };
+
+  cp_async_wait<0>();
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();   // barriers initialised, TMEM allocated, Q staged
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    stage_k(0);
+    stage_v(0);
+    if (n_chunks > 1) stage_v(1);
+    issue_s(0, tmem);
+  }
+  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  const uint32_t t_s = t_row + half * 32;                 // this thread's 32 S columns
+  const uint32_t t_o = t_row + 64 + half * (DH / 2);      // this thread's DH/2 O columns
+
+  float m_ref = -INFINITY, l_part = 0.f;
+
+  for (int c = 0; c < n_chunks; ++c) {
+    int nk, key0, tm_row_unused; bool own;
+    chunk_keys(c, nk, key0, own, tm_row_unused);
+    const int nk16 = (nk + 15) & ~15;
+
+    mbar_wait(&bar_s, static_cast<uint32_t>(c & 1));
+    tc_fence_after();
+    // ---- this thread's 32 keys of the row
+    float sv[32];
+    if (half * 32 < nk16) {   // warp-uniform
+      uint32_t raw[32];
+      tmem_ld32(t_s, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(raw[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sv[i] = 0.f;
+    }
+    int j_lo = 0, j_hi = nk - 1;
+    if (own) {
+      j_lo = max(0, seq_lo - key0);
+      j_hi = min(nk - 1, rt - key0);
+    }
+    const bool any_vis = j_hi >= j_lo;
+    const unsigned span = any_vis ? static_cast<unsigned>(j_hi - j_lo) : 0u;
+    float cmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int j = half * 32 + i;
+      bool vis = any_vis && static_cast<unsigned>(j - j_lo) <= span;
+      if (own && p.key_valid && vis) vis = p.key_valid[key0 + j] != 0;
+      const float val = vis ? sv[i] : -INFINITY;
+      sv[i] = val;
+      cmax = fmaxf(cmax, val);
+    }
+    s_x[half][r] = cmax;
+    tc_fence_before();
+    __syncthreads();   // [A] every S(c) value is in registers: the S columns and the K buffer are free
+    if (tid == 0 && c + 1 < n_chunks) stage_k(c + 1);
+    const float cmax_s = fmaxf(s_x[0][r], s_x[1][r]) * p.scale_log2;   // -inf * positive = -inf
+
+    // ---- Oc = P V of the previous chunk has to be complete before P / O are touched
+    if (c > 0) {
+      mbar_wait(&bar_o, static_cast<uint32_t>((c - 1) & 1));
+      tc_fence_after();
+      if (tid == 0 && c + 1 < n_chunks) stage_v(c + 1);   // its buffer was read by chunk c-1
+    }
+    // ---- lazy rescale of O (TMEM) and of the running sum
+    float corr = 1.f;
+    bool grow = false;
+    if (c == 0) {
+      m_ref = cmax_s;
+    } else if (cmax_s > m_ref + kGrow) {
+      grow = true;
+      corr = exp2f(m_ref - cmax_s);   // 0 when nothing was visible before
+      m_ref = cmax_s;
+      l_part *= corr;
+    }
+    if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll
+      for (int h = 0; h < DH / 64; ++h) {
+        uint32_t raw[32];
+        tmem_ld32(t_o + h * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
+        tmem_st32(t_o + h * 32, raw);
+      }
+      tmem_st_wait();
+    }
+    // ---- P for this thread's 32 keys
+    const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+    float csum = 0.f;
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p0 = exp2f(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
+        const float p1 = exp2f(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
+        csum += p0 + p1;
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+        pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      if (half * 32 + j8 * 8 < nk16) *reinterpret_cast<uint4*>(s_p + sw128_offset(r, half * 32 + j8 * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    l_part += csum;
+
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();   // [B] P written, O rescaled
+    if (tid == 0) {
+      mbar_wait(&bar_v[c & 1], static_cast<uint32_t>((c >> 1) & 1));
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16_ex(128, DH, 1);
+      const uint32_t v_base = smem_u32(s_v) + (c & 1) * kSub * 8192;
+      for (int kk = 0; kk < nk16 / 16; ++kk) {
+        const uint64_t da = make_smem_desc_sw128(smem_u32(s_p) + kk * 32);
+        const uint64_t db = make_smem_desc_raw(v_base + kk * 2048, 8192, 1024);
+        umma_bf16<1>(tmem + 64, da, db, idesc, (c > 0 || kk != 0) ? 1u : 0u);
+      }
+      umma_commit(&bar_o);
+      if (c + 1 < n_chunks) issue_s(c + 1, tmem);
+    }
+  }
+
+  // ---- O / l -> bf16
+  mbar_wait(&bar_o, static_cast<uint32_t>((n_chunks - 1) & 1));
+  tc_fence_after();
+  s_x[half][r] = l_part;
+  __syncthreads();
+  const float l = s_x[0][r] + s_x[1][r];
+  const float inv = l > 0.f ? 1.0f / l : 0.f;
+  __nv_bfloat16* dst = p.o + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH + half * (DH / 2);
+#pragma unroll
+  for (int h = 0; h < DH / 64; ++h) {
+    uint32_t raw[32];
+    tmem_ld32(t_o + h * 32, raw);
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(raw[c8 * 8 + 2 * e]) * inv, __uint_as_float(raw[c8 * 8 + 2 * e + 1]) * inv);
+          pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        *reinterpret_cast<uint4*>(dst + h * 32 + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc<1>(tmem, kTcTmemCols);
+}
+
 // Host: blocks of 128 / G consecutive tokens over every prefix-sharing group of consecutive sequences, plus the
 // per-token "first token of my sequence" table.
 inline void build_attn_works_tc(const AttnSeq* seqs, int n_seqs, int group, std::vector<AttnWorkTc>& works, std::vector<int>& tok_seq_start,
@@ -331,10 +604,27 @@ struct AttnTcMaps {
   CUtensorMap ka, va, kb, vb;
 };
 
+template <int DH>
+inline cudaError_t launch_attention_tc2_impl(const AttnTcMaps& m, const AttnParamsTc& p, dim3 grid, cudaStream_t stream) {
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc2_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc2_smem_bytes<DH>());
+    if (e != cudaSuccess) return e;
+    set = true;
+  }
+  attention_tc2_kernel<DH><<<grid, kTc2Threads, attn_tc2_smem_bytes<DH>(), stream>>>(m.ka, m.va, m.kb, m.vb, p);
+  return cudaGetLastError();
+}
+
 inline cudaError_t launch_attention_tc(const AttnTcMaps& m, const AttnParamsTc& p, int n_works, int n_kv_heads, int head_dim,
-                                       cudaStream_t stream) {
+                                       cudaStream_t stream, int version = 2) {
   if (n_works <= 0) return cudaSuccess;
   dim3 grid(static_cast<unsigned>(n_works), static_cast<unsigned>(n_kv_heads));
+  if (version == 2) {
+    if (head_dim == 128) return launch_attention_tc2_impl<128>(m, p, grid, stream);
+    if (head_dim == 64) return launch_attention_tc2_impl<64>(m, p, grid, stream);
+    return cudaErrorInvalidValue;
+  }
   if (head_dim == 128) {
     static bool set = false;
     if (!set) {

@@ -140,7 +140,8 @@ struct blim_engine {
   // workspaces
   DevBuf x, xn, q, attn, k_own, v_own, act, kp, vp, prefix_last, vis, proj_tmp, lm_a, pred, partial, tgt_logit, logp, uniq_scores;
   DevBuf d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
-  bool attn_tc = true;  // tcgen05 attention (BLIM_ATTN=mma selects the mma.sync kernel)
+  bool attn_tc = true;  // tcgen05 attention (BLIM_ATTN=mma selects the mma.sync kernel, tc1 the first tcgen05 kernel)
+  int attn_tc_version = 2;
   CUtensorMap tm_kp, tm_vp, tm_kown, tm_vown;  // K / V buffers as TMA tensors (tcgen05 attention)
   size_t partial_tiles = 0;
 
@@ -268,6 +269,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
   {
     const char* a = getenv("BLIM_ATTN");
     e->attn_tc = !(a && std::string(a) == "mma");
+    e->attn_tc_version = (a && std::string(a) == "tc1") ? 1 : 2;
   }
   e->gemm.cta_group = cfg->gemm_cta_group == 1 ? 1 : 2;  // default: CTA pairs (cta_group::2)
   auto bad = [&](const char* m) {
@@ -605,7 +607,7 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
       ap.key_valid = run.any_invalid ? e->d_key_valid.as<uint8_t>() : nullptr;
       ap.tok_seq_start = e->d_seq_start.as<int>(); ap.works = e->d_works.as<AttnWorkTc>();
       ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G; ap.scale_log2 = scale_log2;
-      r = launch_attention_tc(maps, ap, n_works, e->NKV, e->DH, st);
+      r = launch_attention_tc(maps, ap, n_works, e->NKV, e->DH, st, e->attn_tc_version);
     } else {
       AttnParams ap;
       ap.q = e->q.as<bf16>(); ap.o = e->attn.as<bf16>();
