@@ -180,11 +180,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_cons
       umma_commit(&bar_s);
     }
     mbar_wait(&bar_s, ph);
+    __syncwarp();
     tc_fence_after();
     // the K buffer is free again: K(c+1) streams in under the softmax and the P V product
     int nk_n = 0, key0_n = 0, row_n = 0; bool own_n = false;
     if (c + 1 < n_chunks) chunk_keys(c + 1, nk_n, key0_n, own_n, row_n);
     if (tid == 0 && c + 1 < n_chunks) stage(s_k, own_n ? &tm_kb : &tm_ka, &bar_k, row_n);
+    __syncwarp();
 
     // ---- softmax of this row over the chunk's keys; P -> smem
     float corr;
@@ -258,6 +260,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_cons
     tc_fence_after();
     // V and P buffers are free: V(c+1) streams in under the accumulation and the next S = Q K^T
     if (tid == 0 && c + 1 < n_chunks) stage(s_v, own_n ? &tm_vb : &tm_va, &bar_v, row_n);
+    __syncwarp();
 #pragma unroll
     for (int h = 0; h < DH / 32; ++h) {
       float t[32];
@@ -429,6 +432,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
     const int nk16 = (nk + 15) & ~15;
 
     mbar_wait(&bar_s, static_cast<uint32_t>(c & 1));
+    __syncwarp();   // the tcgen05.ld / .st below are warp-collective: reconverge after the per-lane spin
     tc_fence_after();
     // ---- this thread's 32 keys of the row
     float sv[32];
@@ -470,6 +474,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
       mbar_wait(&bar_o, static_cast<uint32_t>((c - 1) & 1));
       tc_fence_after();
       if (tid == 0 && c + 1 < n_chunks) stage_v(c + 1);   // its buffer was read by chunk c-1
+      __syncwarp();
     }
     // ---- lazy rescale of O (TMEM) and of the running sum
     float corr = 1.f;
@@ -532,6 +537,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
 
   // ---- O / l -> bf16
   mbar_wait(&bar_o, static_cast<uint32_t>((n_chunks - 1) & 1));
+  __syncwarp();
   tc_fence_after();
   s_x[half][r] = l_part;
   __syncthreads();

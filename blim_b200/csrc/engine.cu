@@ -1279,6 +1279,7 @@ extern "C" int blim_debug_gemm(blim_engine* e, int epilogue, const void* A, cons
     case 2: { EpiStore<bf16, true, true>::Params p{reinterpret_cast<bf16*>(C), N, bias}; r = gemm<EpiStore<bf16, true, true>>(e, a, K, w, K, M, N, K, p, st); break; }
     case 3: { EpiStore<float, false, false>::Params p{reinterpret_cast<float*>(C), N, nullptr}; r = gemm<EpiStore<float, false, false>>(e, a, K, w, K, M, N, K, p, st); break; }
     case 4: { EpiResid::Params p{reinterpret_cast<float*>(C), N}; r = gemm<EpiResid>(e, a, K, w, K, M, N, K, p, st); break; }
+    case 7: { EpiResidT<1>::Params p{reinterpret_cast<float*>(C), N}; r = gemm<EpiResidT<1>>(e, a, K, w, K, M, N, K, p, st); break; }
     case 5: { EpiSwiglu::Params p{reinterpret_cast<bf16*>(C), N / 2}; r = gemm<EpiSwiglu>(e, a, K, w, K, M, N, K, p, st); break; }
     case 6: {
       if (M > e->Tmax) { r = e->fail("debug_gemm lse: M exceeds max_run_tokens"); break; }

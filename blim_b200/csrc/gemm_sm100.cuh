@@ -114,6 +114,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // out[row, col] = act(acc + bias[col])   OutT = __nv_bfloat16 or float
 template <typename OutT, bool kBias, bool kGelu>
 struct EpiStore {
+  static constexpr int kGroups = 2;
   struct Params {
     OutT* out;
     int ldo;
@@ -148,8 +149,10 @@ struct EpiStore {
   }
 };
 
-// resid[row, col] += acc     (fp32 residual stream, in place)
-struct EpiResid {
+// resid[row, col] += acc     (fp32 residual stream, in place).  kGroups = epilogue warpgroups that share a tile.
+template <int kGroupsT>
+struct EpiResidT {
+  static constexpr int kGroups = kGroupsT;
   struct Params {
     float* resid;
     int ldo;
@@ -157,7 +160,7 @@ struct EpiResid {
   __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
     const bool row_ok = row < d.M;
 #pragma unroll 1
-    for (int c = half * (kBN / 2); c < (half + 1) * (kBN / 2); c += 32) {
+    for (int c = half * (kBN / kGroups); c < (half + 1) * (kBN / kGroups); c += 32) {
       float v[32];
       tmem_ld32f(taddr + c, v);
       const int col = n0 + c;
@@ -183,6 +186,8 @@ struct EpiResid {
   }
 };
 
+using EpiResid = EpiResidT<2>;
+
 // Fused QKV projection epilogue: + bias, rotary embedding on Q and K heads (half-split rotation, per-token position
 // looked up in a host-built cos/sin table), Q -> q_out[token], K/V -> kv cache rows kv_slot[token].
 // Column layout of the fused weight: [ Q heads | K heads | V heads ], every head head_dim wide; kBN is a multiple of head_dim.
@@ -192,6 +197,7 @@ struct EpiResid {
 // the two items that share one rotary chunk (head_dim 128: chunk = half, both heads; head_dim 64: heads 2*half, 2*half+1).
 template <int kHeadDim>
 struct EpiQkvRope {
+  static constexpr int kGroups = 2;
   struct Params {
     __nv_bfloat16* q_out;  // [M, n_q]
     __nv_bfloat16* k_out;  // [slots, n_kv]
@@ -259,6 +265,7 @@ struct EpiQkvRope {
 // SwiGLU: the fused gate|up weight is interleaved in 128-row blocks, so tile n holds gate[128n..128n+127] in columns
 // 0..127 and up[128n..128n+127] in columns 128..255.  act[row, 128 n + c] = silu(gate) * up.
 struct EpiSwiglu {
+  static constexpr int kGroups = 2;
   struct Params {
     __nv_bfloat16* act;  // [M, I]
     int ldo;             // = I
@@ -283,6 +290,7 @@ struct EpiSwiglu {
 // Fused "logits never materialised" epilogue: per row, the running (max, sum-exp) over this tile's columns of
 // scale*acc, plus the scaled logit of the row's target column if it falls into this tile.
 struct EpiLse {
+  static constexpr int kGroups = 2;
   struct Params {
     float2* partial;    // [M, 2 * n_tiles] (max, sumexp) per half tile
     float* tgt_logit;   // [M]
@@ -365,7 +373,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_tfull[i], 1);
-      mbar_init(&bar_tempty[i], 256 * kCtaGroup);
+      mbar_init(&bar_tempty[i], 128 * Epi::kGroups * kCtaGroup);
     }
     fence_barrier_init();
   }
@@ -425,8 +433,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       if constexpr (kCtaGroup == 1) umma_commit(&bar_tfull[acc]); else umma_commit_pair(&bar_tfull[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 4) {
-    // ===================================================== epilogue (2 warpgroups x 4 warps; 4 warps = 128 TMEM lanes = 128 rows)
+  } else if (warp >= 4 && (warp - 4) < 4 * Epi::kGroups) {
+    // ===================================================== epilogue (kGroups warpgroups x 4 warps; 4 warps = 128 TMEM lanes = 128 rows)
     const int ew = (warp - 4) & 3;       // TMEM lane quadrant (= warp % 4)
     const int half = (warp - 4) >> 2;    // which half of the tile's columns / work items
     int acc = 0;

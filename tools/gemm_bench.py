@@ -14,14 +14,15 @@ def main():
     eng = Engine(ModelConfig.tiny(), max_run_tokens=16384, max_prefix_tokens=256)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     shapes = [(8192, 4608, 3584, 0), (8192, 3584, 3584, 0), (8192, 37888, 3584, 5), (8192, 3584, 18944, 0), (16384, 37888, 3584, 5),
-              (4096, 152064, 3584, 6), (8192, 8192, 8192, 0)]
+              (4096, 152064, 3584, 6), (8192, 8192, 8192, 0), (27072, 3584, 18944, 4), (27072, 3584, 18944, 7), (27072, 3584, 3584, 4),
+              (27072, 3584, 3584, 7), (27072, 3584, 18944, 4), (27072, 3584, 18944, 7)]
     out = []
     for M, N, K, epi in shapes:
         A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
         W = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
         tgt = torch.randint(0, N, (M,), device="cuda", dtype=torch.int32)
-        for cg in (1, 2):
-            C = None
+        for cg in ((2,) if epi in (4, 7) else (1, 2)):
+            C = torch.zeros(M, N, device="cuda") if epi in (4, 7) else None
             ts = []
             for it in range(6):
                 flush.zero_()
