@@ -14,6 +14,7 @@ N > 1: launched by torchrun, one rank per GPU; pairs are sharded by prefix owner
 one NCCL all-gather of compact scores per score kind.
 """
 import argparse
+import contextlib
 import json
 import math
 import os
@@ -38,6 +39,10 @@ WORKLOADS = {
                desc="C2: VideoChat-Flash-Qwen2-7B random-init, MSRVTT-1k shape, 1000 queries x top-16, both directions + CPN (6 matrices)"),
     "c3": dict(model="qwen2_7b", dataset="didemo", n=None, topk=16, alpha=(0.0, 0.9), c=(0.9, 0.2, 0.9, 0.9), n_clips=None,
                desc="C3: 7B, DiDeMo shape (1004 queries, long captions), top-16, CPN + ensemble"),
+    "c4": dict(model="qwen2_7b", dataset="activitynet", n=None, topk=16, alpha=(0.2, 0.9), c=(1.0, 0.4, 0.9, 0.8), n_clips=16,
+               desc="C4: 7B, ActivityNet val_1 shape (4917 videos x 16 clips = 1024 visual tokens, long captions), top-16 (sized for 8 GPUs; use --n to subsample)"),
+    "c5": dict(model="qwen2_7b", dataset="lsmdc", n=None, topk=64, alpha=(0.2, 1.0), c=(1.0, 0.6, 0.9, 0.6), n_clips=None,
+               desc="C5: 7B, LSMDC test shape (1000 queries), top-64 (use --topk 16/32/64 for the sweep)"),
     "tiny": dict(model="tiny", dataset="msrvtt", n=64, topk=8, alpha=(0.0, 0.8), c=(1.0, 0.6, 0.8, 0.4), n_clips=None,
                  desc="tiny: 2-layer hidden-256 model, 64 queries x top-8 (debug)"),
 }
@@ -51,6 +56,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the number of queries/videos (debug)")
+    ap.add_argument("--topk", type=int, default=0, help="override the workload's top-k")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cta-group", type=int, default=0)
@@ -278,7 +284,7 @@ def main():
         del t
     eng.set_rope(torch.float32)
     corpus = synth.make_corpus(cfg, wl["dataset"], n=args.n or wl["n"], n_clips=wl["n_clips"], seed=1, feat_device=dev)
-    n, topk = corpus.n, wl["topk"]
+    n, topk = corpus.n, (args.topk or wl["topk"])
     alpha, c = wl["alpha"], wl["c"]
 
     # device-resident inputs for `value`
@@ -359,7 +365,8 @@ def main():
 
         def step_e2e():
             model._corpus_keys.clear()
-            r = evalloop.val_one_epoch(model, loader, None, dev, 0, None, tokenizer=None, args=eargs)
+            with contextlib.redirect_stdout(sys.stderr):   # the JSON line is the only thing on stdout
+                r = evalloop.val_one_epoch(model, loader, None, dev, 0, None, tokenizer=None, args=eargs)
             return r
 
         step_e2e()
