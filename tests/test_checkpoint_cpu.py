@@ -1,0 +1,44 @@
+"""LoRA merge loader: W' = W + alpha/r * B @ A under the PEFT key names the reference produces."""
+import pytest
+import torch
+
+from blim_b200.checkpoint import _plain_name, merge_lora
+
+
+def test_plain_names():
+    assert _plain_name("base_model.model.model.layers.3.self_attn.q_proj.base_layer.weight") == "model.layers.3.self_attn.q_proj.weight"
+    assert _plain_name("base_model.model.model.mm_projector.mlp.base_model.model.0.base_layer.bias") == "model.mm_projector.mlp.0.bias"
+    assert _plain_name("base_model.model.visual_head.weight") == "visual_head.weight"
+    assert _plain_name("model.norm.weight") == "model.norm.weight"
+
+
+def test_merge_matches_adapter_forward():
+    g = torch.Generator().manual_seed(0)
+    r, alpha = 8, 32
+    base = {"model.layers.0.self_attn.q_proj.weight": torch.randn(64, 48, generator=g).bfloat16(),
+            "model.mm_projector.tvg_mlp.2.weight": torch.randn(48, 48, generator=g).bfloat16(),
+            "lm_head.weight": torch.randn(100, 48, generator=g).bfloat16(),
+            "visual_head.weight": torch.zeros(16, 48).bfloat16(),
+            "model.norm.weight": torch.ones(48).bfloat16()}
+    ckpt = {}
+    adapters = {"base_model.model.model.layers.0.self_attn.q_proj": (64, 48),
+                "base_model.model.model.mm_projector.tvg_mlp.base_model.model.2": (48, 48),
+                "base_model.model.lm_head": (100, 48)}
+    for stem, (o, i) in adapters.items():
+        ckpt[stem + ".lora_A.default.weight"] = torch.randn(r, i, generator=g) * 0.1
+        ckpt[stem + ".lora_B.default.weight"] = torch.randn(o, r, generator=g) * 0.1
+    ckpt["base_model.model.visual_head.weight"] = torch.randn(16, 48, generator=g)
+    merged, names = merge_lora(base, ckpt, r, alpha, dtype=torch.float32)
+    assert sorted(names) == sorted(["model.layers.0.self_attn.q_proj.weight", "model.mm_projector.tvg_mlp.2.weight", "lm_head.weight"])
+    x = torch.randn(5, 48, generator=g)
+    for stem, _ in adapters.items():
+        from blim_b200.checkpoint import _plain_name as pn
+        W = base[pn(stem) + ".weight"].float()
+        A, B = ckpt[stem + ".lora_A.default.weight"], ckpt[stem + ".lora_B.default.weight"]
+        want = x @ W.t() + (alpha / r) * (x @ A.t()) @ B.t()          # PEFT's adapter forward
+        got = x @ merged[pn(stem) + ".weight"].t()
+        assert torch.allclose(got, want, atol=1e-4)
+    assert torch.equal(merged["visual_head.weight"], ckpt["base_model.model.visual_head.weight"])
+    assert torch.equal(merged["model.norm.weight"], base["model.norm.weight"])
+    with pytest.raises(ValueError):
+        merge_lora(base, ckpt, 4, alpha)
