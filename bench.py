@@ -297,7 +297,7 @@ def main():
     distributed = world > 1
 
     def step_device():
-        plan = retrieval.PairPlan(v2t_iv2, t2v_iv2, topk, dev)
+        plan = retrieval.PairPlan(v2t_iv2, t2v_iv2, topk, dev, engine=eng)
         s = retrieval.score_all(model, plan, cpn=True, full=True, distributed=distributed)
         t2v_c, v2t_c = retrieval.compact_terms(plan, s, cpn=True, full=True)
         res, detail = evalloop.fused_rerank(eng, t2v_c, v2t_c, t2v_iv2, v2t_iv2, alpha, c, cpn=True, zero_shot=False)

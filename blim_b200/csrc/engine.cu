@@ -1215,6 +1215,24 @@ extern "C" int blim_rank_dense(blim_engine* e, const float* mat, int n_rows, int
   return 0;
 }
 
+extern "C" int blim_topk_rows(blim_engine* e, const float* mat, int n_rows, int n_cols, int k, int32_t* idx_out, float* val_out, void* stream) {
+  if (!e) return 1;
+  if (!mat || !idx_out || !val_out || n_rows < 0 || n_cols <= 0 || k <= 0 || k > n_cols) return e->fail("bad topk arguments");
+  if (n_rows == 0) return 0;
+  CKE(cudaSetDevice(e->device));
+  const int warps = 4;
+  const size_t smem = static_cast<size_t>(warps) * (n_cols * sizeof(float) + ((n_cols + 31) / 32) * sizeof(unsigned));
+  if (smem > 200 * 1024) return e->fail("topk: row too wide for shared memory");
+  static bool attr = false;
+  if (!attr) {
+    CKE(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  topk_rows_kernel<<<(n_rows + warps - 1) / warps, warps * 32, smem, S(stream)>>>(mat, n_rows, n_cols, k, idx_out, val_out);
+  CKL();
+  return 0;
+}
+
 extern "C" int blim_scatter_scores(blim_engine* e, float* dense, int n_rows, int n_cols, int do_fill, float fill, const int32_t* row,
                                    const int32_t* col, const float* val, int64_t n, void* stream) {
   if (!e) return 1;

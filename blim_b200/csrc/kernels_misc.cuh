@@ -244,6 +244,43 @@ __global__ void scatter_scores_kernel(float* __restrict__ dense, int n_cols, con
   if (i < n) dense[static_cast<size_t>(row[i]) * n_cols + col[i]] = val[i];
 }
 
+// ------------------------------------------------------------------------------------------------ stage-1 candidates
+// Per-row top-k of the InternVideo2 similarity rows (reference: sims.topk(k), retrieval_utils.py:52,117): one warp per row,
+// k rounds of a warp arg-max over the row staged in shared memory (ties: lowest column first), results in descending order.
+__global__ void topk_rows_kernel(const float* __restrict__ mat, int n_rows, int n_cols, int k, int* __restrict__ idx_out,
+                                 float* __restrict__ val_out) {
+  extern __shared__ float smem_tk[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const int row = blockIdx.x * warps + warp;
+  float* vals = smem_tk + static_cast<size_t>(warp) * n_cols;
+  unsigned* taken = reinterpret_cast<unsigned*>(smem_tk + static_cast<size_t>(warps) * n_cols) + static_cast<size_t>(warp) * ((n_cols + 31) / 32);
+  if (row >= n_rows) return;
+  for (int i = lane; i < n_cols; i += 32) vals[i] = mat[static_cast<size_t>(row) * n_cols + i];
+  for (int i = lane; i < (n_cols + 31) / 32; i += 32) taken[i] = 0u;
+  __syncwarp();
+  for (int r = 0; r < k; ++r) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < n_cols; i += 32) {
+      if (taken[i >> 5] & (1u << (i & 31))) continue;
+      const float v = vals[i];
+      if (bi == 0x7fffffff || v > best) { best = v; bi = i; }   // strided scan visits indices in increasing order
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      idx_out[static_cast<size_t>(row) * k + r] = bi;
+      val_out[static_cast<size_t>(row) * k + r] = best;
+      taken[bi >> 5] |= (1u << (bi & 31));
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ CPN + ensemble + rerank
 // Reference: val_one_epoch (training_utils.py:154-165) + get_recall (training_utils.py:173-221).
 // numpy semantics reproduced operation by operation: Python-float coefficients meet float32 arrays as float32 scalars,

@@ -262,6 +262,17 @@ class Engine:
                                                  ctypes.c_void_p(rank.data_ptr()), ctypes.c_void_p(zero.data_ptr()), self._stream()))
         return rank, zero
 
+    def topk_rows(self, mat, k):
+        """Per-row top-k of a dense fp32 matrix on the device -> (idx int64 [rows, k], val fp32 [rows, k]), descending."""
+        with torch.cuda.device(self.device):
+            m = self._dev(mat, torch.float32)
+            k = min(int(k), m.shape[1])
+            idx = torch.empty(m.shape[0], k, dtype=torch.int32, device=self.device)
+            val = torch.empty(m.shape[0], k, dtype=torch.float32, device=self.device)
+            self._check(self.lib.blim_topk_rows(self.h, ctypes.c_void_p(m.data_ptr()), m.shape[0], m.shape[1], k,
+                                                ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(val.data_ptr()), self._stream()))
+        return idx.long(), val
+
     def scatter_scores(self, n_rows, n_cols, row, col, val, fill=-100.0, dense=None):
         """torch.full((n_rows, n_cols), fill) then dense[row, col] = val  (reference retrieval_utils.py:219,110)."""
         with torch.cuda.device(self.device):

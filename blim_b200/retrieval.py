@@ -46,20 +46,19 @@ def _engine_model(model):
     return m
 
 
-def _rows_topk(iterator, topk, device):
+def _rows_topk(iterator, topk, device, engine):
     rows = [r if torch.is_tensor(r) else torch.as_tensor(r) for r in iterator]
     if not rows:
         return None
     sims = torch.stack(rows, 0).to(device)
-    k = min(sims.shape[1], topk)
-    return sims.topk(k=k, dim=1).indices  # [rows, k], same per-row result as sims.topk(k, dim=0) (ru:52,117)
+    return engine.topk_rows(sims.float(), topk)[0]  # [rows, k], same per-row result as sims.topk(k, dim=0) (ru:52,117)
 
 
 def _score_rows(scores_x, iterator, start, input_ids, attention_masks, labels, video, video_vocab, tvg_video_labels, model, device, args,
                 forward_type, cpn, rows_are_videos):
     m = _engine_model(model)
     eng = m.engine
-    idx = _rows_topk(iterator, args.topk, eng.device)
+    idx = _rows_topk(iterator, args.topk, eng.device, eng)
     if idx is None:
         return scores_x
     n_rows, k = idx.shape
@@ -103,9 +102,13 @@ class PairPlan:
     Device tensors for the kernels and numpy copies for the host-side scheduler (one D2H at construction, so nothing
     later has to synchronise the stream to look at indices)."""
 
-    def __init__(self, v2t_iv2, t2v_iv2, topk, device):
-        self.v2t_idx = v2t_iv2.to(device).topk(k=min(v2t_iv2.shape[1], topk), dim=1).indices  # [Nv, k] text ids
-        self.t2v_idx = t2v_iv2.to(device).topk(k=min(t2v_iv2.shape[1], topk), dim=1).indices  # [Nt, k] video ids
+    def __init__(self, v2t_iv2, t2v_iv2, topk, device, engine=None):
+        if engine is not None:   # stage-1 candidates on the device with the engine's warp-level top-k kernel
+            self.v2t_idx = engine.topk_rows(v2t_iv2, topk)[0]                                     # [Nv, k] text ids
+            self.t2v_idx = engine.topk_rows(t2v_iv2, topk)[0]                                     # [Nt, k] video ids
+        else:                    # host-logic tests without a GPU
+            self.v2t_idx = v2t_iv2.to(device).topk(k=min(v2t_iv2.shape[1], topk), dim=1).indices
+            self.t2v_idx = t2v_iv2.to(device).topk(k=min(t2v_iv2.shape[1], topk), dim=1).indices
         nv, k = self.v2t_idx.shape
         nt = self.t2v_idx.shape[0]
         self.n_videos, self.n_texts, self.k = nv, nt, k
@@ -231,7 +234,7 @@ def evaluation(model, data_loader, device, tokenizer, args):
         m.ensure_vocab(data_loader.dataset.video_vocab, tvg_video_labels)
     m.set_tvg_prefix_length(data_loader.dataset.tvg_prefix_length)      # retrieval_utils.py:210
 
-    plan = PairPlan(v2t_iv2.float(), t2v_iv2.float(), args.topk, eng.device)
+    plan = PairPlan(v2t_iv2.float(), t2v_iv2.float(), args.topk, eng.device, engine=eng)
     s = score_all(model, plan, cpn=bool(args.cpn), full=full, distributed=bool(getattr(args, "distributed", False)))
     t2v_c, v2t_c = compact_terms(plan, s, cpn=bool(args.cpn), full=full)
     m.last_plan, m.last_compact = plan, (t2v_c, v2t_c)                  # kept on the device for the fused rerank

@@ -121,6 +121,9 @@ int blim_fuse_rerank(blim_engine* e, const blim_fuse_cfg* cfg, const int32_t* ca
 /* get_recall's rank search on a dense score matrix [n_rows, n_cols] fp32 (device). */
 int blim_rank_dense(blim_engine* e, const float* mat, int n_rows, int n_cols, int row0, int32_t* gt_rank_out, int32_t* zero_count,
                     void* stream);
+/* Stage-1 candidates: per-row top-k (descending, ties lowest column first) of a dense fp32 similarity matrix -- replaces
+ * sims.topk(k) on the InternVideo2 rows (retrieval_utils.py:52,117).  All device arrays; idx int32 / val fp32 [n_rows, k]. */
+int blim_topk_rows(blim_engine* e, const float* mat, int n_rows, int n_cols, int k, int32_t* idx_out, float* val_out, void* stream);
 /* dense[row[i], col[i]] = val[i] after an optional fill (retrieval_utils.py:219, 110, 152); all device arrays. */
 int blim_scatter_scores(blim_engine* e, float* dense, int n_rows, int n_cols, int do_fill, float fill, const int32_t* row,
                         const int32_t* col, const float* val, int64_t n, void* stream);

@@ -209,3 +209,18 @@ def test_fuse_rerank_random_large():
         assert np.array_equal(dense.cpu().numpy(), mats["query_likelihood"])
     finally:
         eng.close()
+
+
+def test_topk_rows_matches_torch():
+    eng = Engine(ModelConfig.tiny(), max_run_tokens=512, max_prefix_tokens=256)
+    try:
+        for n_rows, n_cols, k in ((7, 5, 5), (100, 1000, 16), (33, 4917, 64), (4, 77, 1)):
+            g = torch.Generator(device="cuda").manual_seed(n_cols)
+            m = torch.randn(n_rows, n_cols, generator=g, device="cuda")
+            idx, val = eng.topk_rows(m, k)
+            ref = m.topk(k, dim=1)
+            assert torch.equal(val, ref.values) and torch.equal(idx, ref.indices), (n_rows, n_cols, k)
+        m = torch.tensor([[1.0, 3.0, 3.0, 2.0, 3.0]], device="cuda")      # ties: lowest column first
+        assert eng.topk_rows(m, 4)[0].tolist() == [[1, 2, 4, 3]]
+    finally:
+        eng.close()
