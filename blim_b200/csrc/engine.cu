@@ -60,6 +60,7 @@ struct DevBuf {
 
 struct LayerW {
   DevBuf w_qkv, w_o, w_gu, w_down, b_qkv, ln1, ln2;
+  bool folded = false;  // input_layernorm / post_attention_layernorm weights folded into w_qkv / w_gu (fused RMSNorm)
 };
 struct ProjW {
   DevBuf w0, b0, w2, b2;
@@ -142,6 +143,8 @@ struct blim_engine {
   DevBuf d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
   bool attn_tc = true;  // tcgen05 attention (BLIM_ATTN=mma selects the mma.sync kernel, tc1 the first tcgen05 kernel)
   int attn_tc_version = 2;
+  bool fuse_norm = true;  // RMSNorm fused into the GEMMs around it (BLIM_FUSE_NORM=0: standalone rmsnorm kernel)
+  DevBuf ssq, rstd;
   CUtensorMap tm_kp, tm_vp, tm_kown, tm_vown;  // K / V buffers as TMA tensors (tcgen05 attention)
   size_t partial_tiles = 0;
 
@@ -208,14 +211,14 @@ static int gemm(blim_engine* e, const bf16* A, int lda, const bf16* W, int ldw, 
 }
 
 static int gemm_qkv(blim_engine* e, const bf16* A, const LayerW& w, int M, bf16* q_out, bf16* k_out, bf16* v_out, const int* pos,
-                    cudaStream_t st) {
+                    const float* rstd, cudaStream_t st) {
   if (e->DH == 128) {
     EpiQkvRope<128>::Params p{q_out, k_out, v_out, w.b_qkv.as<float>(), pos, nullptr, e->rope_cos.as<float>(), e->rope_sin.as<float>(),
-                              e->NQ, e->NKVD, e->rope_n};
+                              e->NQ, e->NKVD, e->rope_n, rstd};
     return gemm<EpiQkvRope<128>>(e, A, e->H, w.w_qkv.as<bf16>(), e->H, M, e->NQKV, e->H, p, st);
   }
   EpiQkvRope<64>::Params p{q_out, k_out, v_out, w.b_qkv.as<float>(), pos, nullptr, e->rope_cos.as<float>(), e->rope_sin.as<float>(),
-                           e->NQ, e->NKVD, e->rope_n};
+                           e->NQ, e->NKVD, e->rope_n, rstd};
   return gemm<EpiQkvRope<64>>(e, A, e->H, w.w_qkv.as<bf16>(), e->H, M, e->NQKV, e->H, p, st);
 }
 
@@ -228,7 +231,7 @@ extern "C" void blim_destroy(blim_engine* e) {
   DevBuf* bufs[] = {&e->embed, &e->lm_head, &e->visual_head, &e->norm, &e->rope_cos, &e->rope_sin, &e->feats, &e->vocab, &e->tvg_vis,
                     &e->x, &e->xn, &e->q, &e->attn, &e->k_own, &e->v_own, &e->act, &e->kp, &e->vp, &e->prefix_last, &e->vis,
                     &e->proj_tmp, &e->lm_a, &e->pred, &e->partial, &e->tgt_logit, &e->logp, &e->uniq_scores, &e->d_tok_src,
-                    &e->d_tok_pos, &e->d_key_valid, &e->d_seqs, &e->d_works, &e->d_idx, &e->d_targets, &e->d_row_off, &e->d_map, &e->d_seq_start};
+                    &e->d_tok_pos, &e->d_key_valid, &e->d_seqs, &e->d_works, &e->d_idx, &e->d_targets, &e->d_row_off, &e->d_map, &e->d_seq_start, &e->ssq, &e->rstd};
   for (DevBuf* b : bufs) b->release();
   for (LayerW& l : e->layers) {
     l.w_qkv.release(); l.w_o.release(); l.w_gu.release(); l.w_down.release(); l.b_qkv.release(); l.ln1.release(); l.ln2.release();
@@ -270,6 +273,8 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
     const char* a = getenv("BLIM_ATTN");
     e->attn_tc = !(a && std::string(a) == "mma");
     e->attn_tc_version = (a && std::string(a) == "tc1") ? 1 : 2;
+    const char* f = getenv("BLIM_FUSE_NORM");
+    e->fuse_norm = !(f && std::string(f) == "0");
   }
   e->gemm.cta_group = cfg->gemm_cta_group == 1 ? 1 : 2;  // default: CTA pairs (cta_group::2)
   auto bad = [&](const char* m) {
@@ -294,7 +299,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
       {&e->lm_a, T * e->H * 2}, {&e->pred, T * e->MM * 2}, {&e->tgt_logit, T * 4}, {&e->logp, T * 4},
       {&e->d_tok_src, T * 4}, {&e->d_tok_pos, T * 4}, {&e->d_key_valid, T}, {&e->d_seqs, T * sizeof(AttnSeq)},
       {&e->d_works, (T * e->G / kAttnRows + T + 1) * sizeof(AttnWorkTc)}, {&e->d_idx, T * 4}, {&e->d_targets, T * 4},
-      {&e->d_row_off, (T + 1) * 4}, {&e->d_seq_start, T * 4}};
+      {&e->d_row_off, (T + 1) * 4}, {&e->d_seq_start, T * 4}, {&e->ssq, T * 2 * static_cast<size_t>((e->H + kBN - 1) / kBN) * 4}, {&e->rstd, T * 4}};
   for (auto& a : allocs) {
     cudaError_t r = a.b->reserve(a.bytes);
     if (r != cudaSuccess) {
@@ -386,6 +391,10 @@ extern "C" int blim_load_weight(blim_engine* e, const char* name_c, const void* 
     if (li < 0 || li >= e->NL) return e->fail("layer index out of range: " + name);
     LayerW& w = e->layers[li];
     const std::string rest = name.substr(dot + 1);
+    if (w.folded && (rest.find("q_proj.weight") != std::string::npos || rest.find("k_proj.weight") != std::string::npos ||
+                     rest.find("v_proj.weight") != std::string::npos || rest.find("gate_proj") != std::string::npos ||
+                     rest.find("up_proj") != std::string::npos || rest.find("layernorm") != std::string::npos))
+      return e->fail("layer " + std::to_string(li) + " is already finalised (norm weights folded into its GEMM weights): create a new engine to reload " + name);
     if (rest == "self_attn.q_proj.weight") { if (!is2(NQ, H)) return shape_err(); return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NQ, H, 0, 0, 0, st); }
     if (rest == "self_attn.k_proj.weight") { if (!is2(NKVD, H)) return shape_err(); return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NKVD, H, NQ, 0, 0, st); }
     if (rest == "self_attn.v_proj.weight") { if (!is2(NKVD, H)) return shape_err(); return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NKVD, H, NQ + NKVD, 0, 0, st); }
@@ -516,6 +525,16 @@ static int check_ready(blim_engine* e) {
       return e->fail("weights of layer " + std::to_string(l) + " not loaded");
   }
   if (!e->rope_cos.p) return e->fail("rotary table not set (blim_set_rope)");
+  if (e->fuse_norm) {
+    for (int l = 0; l < e->NL; ++l) {
+      LayerW& w = e->layers[l];
+      if (w.folded) continue;
+      fold_norm_weight_kernel<<<2048, 256>>>(w.w_qkv.as<bf16>(), w.ln1.as<float>(), static_cast<size_t>(e->NQKV), e->H);
+      fold_norm_weight_kernel<<<2048, 256>>>(w.w_gu.as<bf16>(), w.ln2.as<float>(), 2 * static_cast<size_t>(e->I), e->H);
+      w.folded = true;
+    }
+    CKE(cudaDeviceSynchronize());  // one-time (legacy-stream launches above): everything later is stream-ordered
+  }
   return 0;
 }
 
@@ -582,14 +601,34 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
     CKL();
   }
   const size_t kv_layer = static_cast<size_t>(e->Pmax) * e->NKVD;
+  const bool fuse = e->fuse_norm;
+  const int n_parts = 2 * ((e->H + kBN - 1) / kBN);
+  const float* rstd = fuse ? e->rstd.as<float>() : nullptr;
+  auto rowprep = [&](const float* x, int R) -> int {   // xn = bf16(x), rstd = 1/rms(x)
+    rowprep_kernel<<<R, 256, 0, st>>>(e->xn.as<bf16>(), e->rstd.as<float>(), x, R, e->H, e->cfg.rms_norm_eps);
+    CKL();
+    return 0;
+  };
+  auto resid_gemm = [&](const bf16* A, int lda, const bf16* W, int K, float* x, int R, bool want_norm) -> int {
+    if (want_norm) {   // x += A W^T, xn = bf16(x), rstd = 1/rms(x)  (first half of the next RMSNorm)
+      EpiResidNorm::Params pn{x, e->xn.as<bf16>(), e->ssq.as<float>(), e->H};
+      CKR(gemm<EpiResidNorm>(e, A, lda, W, lda, R, e->H, K, pn, st));
+      rstd_rows_kernel<<<(R + 255) / 256, 256, 0, st>>>(e->rstd.as<float>(), e->ssq.as<float>(), R, n_parts, e->H, e->cfg.rms_norm_eps);
+      CKL();
+      return 0;
+    }
+    EpiResid::Params pr{x, e->H};
+    return gemm<EpiResid>(e, A, lda, W, lda, R, e->H, K, pr, st);
+  };
+  if (fuse) CKR(rowprep(e->x.as<float>(), T));
   for (int l = 0; l < e->NL; ++l) {
     const LayerW& w = e->layers[l];
     bf16* kpl = e->kp.as<bf16>() + l * kv_layer;
     bf16* vpl = e->vp.as<bf16>() + l * kv_layer;
     bf16* k_out = to_prefix_cache ? kpl : e->k_own.as<bf16>();
     bf16* v_out = to_prefix_cache ? vpl : e->v_own.as<bf16>();
-    CKR(rmsnorm(e, e->xn.as<bf16>(), e->x.as<float>(), nullptr, nullptr, w.ln1.as<float>(), T, st));
-    CKR(gemm_qkv(e, e->xn.as<bf16>(), w, T, e->q.as<bf16>(), k_out, v_out, e->d_tok_pos.as<int>(), st));
+    if (!fuse) CKR(rmsnorm(e, e->xn.as<bf16>(), e->x.as<float>(), nullptr, nullptr, w.ln1.as<float>(), T, st));
+    CKR(gemm_qkv(e, e->xn.as<bf16>(), w, T, e->q.as<bf16>(), k_out, v_out, e->d_tok_pos.as<int>(), rstd, st));
     const bool prune = last_rows != nullptr && l == e->NL - 1;
     if (prune && last_rows->empty()) break;
     const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(e->DH));
@@ -629,20 +668,19 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
       CKL();
       gather_rows_f32_kernel<<<U, 256, 0, st>>>(e->prefix_last.as<float>(), e->x.as<float>(), e->d_idx.as<int>(), U, e->H);
       CKL();
-      EpiResid::Params pl{e->prefix_last.as<float>(), e->H};
-      CKR(gemm<EpiResid>(e, e->xn.as<bf16>(), e->NQ, w.w_o.as<bf16>(), e->NQ, U, e->H, e->NQ, pl, st));
-      CKR(rmsnorm(e, e->xn.as<bf16>(), e->prefix_last.as<float>(), nullptr, nullptr, w.ln2.as<float>(), U, st));
-      EpiSwiglu::Params psl{e->act.as<bf16>(), e->I};
+      CKR(resid_gemm(e->xn.as<bf16>(), e->NQ, w.w_o.as<bf16>(), e->NQ, e->prefix_last.as<float>(), U, false));
+      if (fuse) CKR(rowprep(e->prefix_last.as<float>(), U));
+      else CKR(rmsnorm(e, e->xn.as<bf16>(), e->prefix_last.as<float>(), nullptr, nullptr, w.ln2.as<float>(), U, st));
+      EpiSwiglu::Params psl{e->act.as<bf16>(), e->I, rstd};
       CKR(gemm<EpiSwiglu>(e, e->xn.as<bf16>(), e->H, w.w_gu.as<bf16>(), e->H, U, 2 * e->I, e->H, psl, st));
-      CKR(gemm<EpiResid>(e, e->act.as<bf16>(), e->I, w.w_down.as<bf16>(), e->I, U, e->H, e->I, pl, st));
+      CKR(resid_gemm(e->act.as<bf16>(), e->I, w.w_down.as<bf16>(), e->I, e->prefix_last.as<float>(), U, false));
       break;
     }
-    EpiResid::Params pr{e->x.as<float>(), e->H};
-    CKR(gemm<EpiResid>(e, e->attn.as<bf16>(), e->NQ, w.w_o.as<bf16>(), e->NQ, T, e->H, e->NQ, pr, st));
-    CKR(rmsnorm(e, e->xn.as<bf16>(), e->x.as<float>(), nullptr, nullptr, w.ln2.as<float>(), T, st));
-    EpiSwiglu::Params ps{e->act.as<bf16>(), e->I};
+    CKR(resid_gemm(e->attn.as<bf16>(), e->NQ, w.w_o.as<bf16>(), e->NQ, e->x.as<float>(), T, fuse));
+    if (!fuse) CKR(rmsnorm(e, e->xn.as<bf16>(), e->x.as<float>(), nullptr, nullptr, w.ln2.as<float>(), T, st));
+    EpiSwiglu::Params ps{e->act.as<bf16>(), e->I, rstd};
     CKR(gemm<EpiSwiglu>(e, e->xn.as<bf16>(), e->H, w.w_gu.as<bf16>(), e->H, T, 2 * e->I, e->H, ps, st));
-    CKR(gemm<EpiResid>(e, e->act.as<bf16>(), e->I, w.w_down.as<bf16>(), e->I, T, e->H, e->I, pr, st));
+    CKR(resid_gemm(e->act.as<bf16>(), e->I, w.w_down.as<bf16>(), e->I, e->x.as<float>(), T, fuse && l + 1 < e->NL));
   }
   return 0;
 }
@@ -1298,7 +1336,7 @@ extern "C" int blim_debug_gemm(blim_engine* e, int epilogue, const void* A, cons
     case 3: { EpiStore<float, false, false>::Params p{reinterpret_cast<float*>(C), N, nullptr}; r = gemm<EpiStore<float, false, false>>(e, a, K, w, K, M, N, K, p, st); break; }
     case 4: { EpiResid::Params p{reinterpret_cast<float*>(C), N}; r = gemm<EpiResid>(e, a, K, w, K, M, N, K, p, st); break; }
     case 7: { EpiResidT<1>::Params p{reinterpret_cast<float*>(C), N}; r = gemm<EpiResidT<1>>(e, a, K, w, K, M, N, K, p, st); break; }
-    case 5: { EpiSwiglu::Params p{reinterpret_cast<bf16*>(C), N / 2}; r = gemm<EpiSwiglu>(e, a, K, w, K, M, N, K, p, st); break; }
+    case 5: { EpiSwiglu::Params p{reinterpret_cast<bf16*>(C), N / 2, nullptr}; r = gemm<EpiSwiglu>(e, a, K, w, K, M, N, K, p, st); break; }
     case 6: {
       if (M > e->Tmax) { r = e->fail("debug_gemm lse: M exceeds max_run_tokens"); break; }
       r = lse_rows(e, a, K, w, K, M, N, K, target, scale, reinterpret_cast<float*>(C), st);

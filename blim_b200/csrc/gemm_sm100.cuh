@@ -188,6 +188,54 @@ struct EpiResidT {
 
 using EpiResid = EpiResidT<2>;
 
+// Residual add fused with the FIRST half of the following RMSNorm (reference: Qwen2DecoderLayer q2:784-789 + Qwen2RMSNorm
+// q2:93-98): x_new = resid + acc is written back in fp32, its bf16 copy `xb` becomes the A operand of the next GEMM
+// (un-normalised: the norm weight is folded into that GEMM's weight columns and 1/rms is applied per row in its
+// epilogue), and the partial sum of squares of this thread's 128 columns goes to ssq[row, 2 * n_tile + half].
+// The partials are reduced in a fixed order (rstd_rows_kernel), so results stay bit-identical under re-batching.
+struct EpiResidNorm {
+  static constexpr int kGroups = 2;
+  struct Params {
+    float* resid;          // [M, N] in / out
+    __nv_bfloat16* xb;     // [M, N] out
+    float* ssq;            // [M, 2 * n_tiles] out
+    int ldo;
+  };
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
+    const bool row_ok = row < d.M;
+    float ss = 0.f;
+#pragma unroll 1
+    for (int c = half * (kBN / 2); c < (half + 1) * (kBN / 2); c += 32) {
+      float v[32];
+      tmem_ld32f(taddr + c, v);
+      const int col = n0 + c;
+      const int valid = d.N - col;
+      if (valid <= 0) continue;
+      if (row_ok) {
+        float* dst = p.resid + static_cast<size_t>(row) * p.ldo + col;
+        if (valid >= 32) {
+          float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 r = d4[i];
+            r.x += v[4 * i]; r.y += v[4 * i + 1]; r.z += v[4 * i + 2]; r.w += v[4 * i + 3];
+            d4[i] = r;
+            v[4 * i] = r.x; v[4 * i + 1] = r.y; v[4 * i + 2] = r.z; v[4 * i + 3] = r.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < valid) { v[i] += dst[i]; dst[i] = v[i]; } else { v[i] = 0.f; }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ss = fmaf(v[i], v[i], ss);
+        store_row32_bf16(p.xb + static_cast<size_t>(row) * p.ldo + col, v, valid);
+      }
+    }
+    if (row_ok) p.ssq[static_cast<size_t>(row) * (2 * d.n_tiles) + 2 * n_tile + half] = ss;
+  }
+};
+
 // Fused QKV projection epilogue: + bias, rotary embedding on Q and K heads (half-split rotation, per-token position
 // looked up in a host-built cos/sin table), Q -> q_out[token], K/V -> kv cache rows kv_slot[token].
 // Column layout of the fused weight: [ Q heads | K heads | V heads ], every head head_dim wide; kBN is a multiple of head_dim.
@@ -208,15 +256,18 @@ struct EpiQkvRope {
     const float* cos_tab;  // [kHeadDim/2][max_pos]
     const float* sin_tab;
     int n_q, n_kv, max_pos;
+    const float* rstd;     // [M] 1/rms of the (un-normalised) A rows, nullptr = A is already normalised
   };
   __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
     constexpr int kHalf = kHeadDim / 2;
     static_assert(kHeadDim == 64 || kHeadDim == 128, "head_dim must be 64 or 128");
     const bool row_ok = row < d.M;
     int pos = 0, slot = 0;
+    float rs = 1.f;
     if (row_ok) {
       pos = __ldg(p.pos + row);
       slot = p.kv_slot ? __ldg(p.kv_slot + row) : row;
+      if (p.rstd) rs = __ldg(p.rstd + row);
     }
     const int j0 = (kHeadDim == 128) ? half * 32 : 0;          // rotary chunk inside the half-dim
     const int head0 = (kHeadDim == 128) ? 0 : half * 2;        // first of the two heads this warpgroup handles
@@ -248,8 +299,8 @@ struct EpiQkvRope {
       tmem_ld32f(taddr + h * kHeadDim + kHalf + j0, hi);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float a = lo[i] + __ldg(p.bias + c0 + j0 + i);
-        const float b = hi[i] + __ldg(p.bias + c0 + kHalf + j0 + i);
+        const float a = fmaf(lo[i], rs, __ldg(p.bias + c0 + j0 + i));
+        const float b = fmaf(hi[i], rs, __ldg(p.bias + c0 + kHalf + j0 + i));
         // q*cos + rotate_half(q)*sin:  first half q1*cos - q2*sin, second half q2*cos + q1*sin
         lo[i] = rope ? a * cs[i] - b * sn[i] : a;
         hi[i] = rope ? b * cs[i] + a * sn[i] : b;
@@ -269,9 +320,11 @@ struct EpiSwiglu {
   struct Params {
     __nv_bfloat16* act;  // [M, I]
     int ldo;             // = I
+    const float* rstd;   // [M] 1/rms of the (un-normalised) A rows, nullptr = A is already normalised
   };
   __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
     const bool row_ok = row < d.M;
+    const float rs = (row_ok && p.rstd) ? __ldg(p.rstd + row) : 1.f;
 #pragma unroll 1
     for (int c = half * 64; c < half * 64 + 64; c += 32) {
       float g[32], u[32];
@@ -279,8 +332,8 @@ struct EpiSwiglu {
       tmem_ld32f(taddr + 128 + c, u);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float x = g[i];
-        g[i] = (x / (1.0f + __expf(-x))) * u[i];
+        const float x = g[i] * rs;
+        g[i] = (x / (1.0f + __expf(-x))) * (u[i] * rs);
       }
       if (row_ok) store_row32_bf16(p.act + static_cast<size_t>(row) * p.ldo + n_tile * 128 + c, g, 32);
     }

@@ -92,6 +92,47 @@ __global__ void rmsnorm_kernel(__nv_bfloat16* __restrict__ out, const float* __r
   }
 }
 
+// Fused-RMSNorm support (see EpiResidNorm in gemm_sm100.cuh).
+// rstd[r] = rsqrt(sum(parts[r, :]) / H + eps): fixed-order reduction of the per-half-tile sums of squares.
+__global__ void rstd_rows_kernel(float* __restrict__ rstd, const float* __restrict__ parts, int R, int n_parts, int H, float eps) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float s = 0.f;
+  for (int i = 0; i < n_parts; ++i) s += parts[static_cast<size_t>(r) * n_parts + i];
+  rstd[r] = rsqrtf(s / static_cast<float>(H) + eps);
+}
+// Entry of a decoder run (and the pruned last layer): xb = bf16(x), rstd = 1/rms(x) for R fp32 rows.
+__global__ void rowprep_kernel(__nv_bfloat16* __restrict__ xb, float* __restrict__ rstd, const float* __restrict__ x, int R, int H, float eps) {
+  const int r = blockIdx.x;
+  if (r >= R) return;
+  const float* src = x + static_cast<size_t>(r) * H;
+  float ss = 0.f;
+  for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(src + c);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(xb + static_cast<size_t>(r) * H + c) = u;
+  }
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) rstd[r] = rsqrtf(v / static_cast<float>(H) + eps);
+  }
+}
+// W[n, k] *= g[k] in place (bf16 weight, fp32 norm weight): folds an RMSNorm weight into the GEMM that consumes its output.
+__global__ void fold_norm_weight_kernel(__nv_bfloat16* __restrict__ w, const float* __restrict__ g, size_t rows, int cols) {
+  const size_t n = rows * cols;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    w[i] = __float2bfloat16(__bfloat162float(w[i]) * g[i % cols]);
+}
+
 // copy selected fp32 rows: dst[r] = src[idx[r]]   (saves the last-prefix-token state of every prefix sequence)
 __global__ void gather_rows_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, const int* __restrict__ idx, int R, int H) {
   const int r = blockIdx.x;
