@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cta-group", type=int, default=0)
+    ap.add_argument("--run-tokens", type=int, default=0, help="engine workspace: tokens per decoder run / prefix-cache rows (0 = engine default)")
     return ap.parse_args()
 
 
@@ -270,7 +271,7 @@ def main():
 
     cfg = ModelConfig.qwen2_7b() if wl["model"] == "qwen2_7b" else ModelConfig.tiny()
     dev = torch.device("cuda", local_rank)
-    model = BlimModel(cfg, device=local_rank, gemm_cta_group=args.cta_group)
+    model = BlimModel(cfg, device=local_rank, gemm_cta_group=args.cta_group, max_run_tokens=args.run_tokens, max_prefix_tokens=args.run_tokens)
     eng = model.engine
     want_cpu = (not args.no_cpu_baseline) and rank == 0 and world == 1
     weights_cpu = {}

@@ -143,7 +143,7 @@ struct blim_engine {
   DevBuf d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
   bool attn_tc = true;  // tcgen05 attention (BLIM_ATTN=mma selects the mma.sync kernel, tc1 the first tcgen05 kernel)
   int attn_tc_version = 2;
-  bool fuse_norm = true;  // RMSNorm fused into the GEMMs around it (BLIM_FUSE_NORM=0: standalone rmsnorm kernel)
+  bool fuse_norm = false;  // BLIM_FUSE_NORM=1: RMSNorm fused into the GEMMs around it (measured slower than the standalone kernel)
   DevBuf ssq, rstd;
   CUtensorMap tm_kp, tm_vp, tm_kown, tm_vown;  // K / V buffers as TMA tensors (tcgen05 attention)
   size_t partial_tiles = 0;
@@ -274,7 +274,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
     e->attn_tc = !(a && std::string(a) == "mma");
     e->attn_tc_version = (a && std::string(a) == "tc1") ? 1 : 2;
     const char* f = getenv("BLIM_FUSE_NORM");
-    e->fuse_norm = !(f && std::string(f) == "0");
+    e->fuse_norm = f && std::string(f) == "1";
   }
   e->gemm.cta_group = cfg->gemm_cta_group == 1 ? 1 : 2;  // default: CTA pairs (cta_group::2)
   auto bad = [&](const char* m) {
