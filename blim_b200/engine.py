@@ -153,13 +153,26 @@ class Engine:
             torch.cuda.synchronize(self.device)
         self.n_videos, self.n_clips = feats.shape[0], feats.shape[1]
 
-    def set_texts(self, which, ids_list, labels_list):
-        """Ragged, pad-stripped token ids (with the -200 image sentinel) and labels (-100 = ignore)."""
+    def set_texts(self, which, ids_list, labels_list, masks_list=None):
+        """Ragged token ids (with the -200 image sentinel) and labels (-100 = ignore); with `masks_list` the entries whose
+        mask is 0 (padding) are stripped first (what prepare_inputs_labels_for_multimodal does, mvf:333-334)."""
+        lens = np.fromiter((len(x) for x in ids_list), dtype=np.int64, count=len(ids_list))
+        if all(torch.is_tensor(x) for x in ids_list):
+            ids = torch.cat(list(ids_list)).numpy().astype(np.int32)
+            labels = torch.cat(list(labels_list)).numpy().astype(np.int32)
+        else:
+            ids = np.concatenate([np.asarray(x, dtype=np.int64) for x in ids_list]).astype(np.int32)
+            labels = np.concatenate([np.asarray(x, dtype=np.int64) for x in labels_list]).astype(np.int32)
+        if masks_list is not None:
+            mask = (torch.cat(list(masks_list)).numpy() if torch.is_tensor(masks_list[0])
+                    else np.concatenate([np.asarray(x) for x in masks_list])).astype(bool)
+            if not mask.all():
+                seg = np.repeat(np.arange(len(lens)), lens)
+                lens = np.bincount(seg[mask], minlength=len(lens)).astype(np.int64)
+                ids, labels = ids[mask], labels[mask]
         off = np.zeros(len(ids_list) + 1, dtype=np.int64)
-        for i, x in enumerate(ids_list):
-            off[i + 1] = off[i] + len(x)
-        ids = np.concatenate([np.asarray(x, dtype=np.int64) for x in ids_list]).astype(np.int32)
-        labels = np.concatenate([np.asarray(x, dtype=np.int64) for x in labels_list]).astype(np.int32)
+        np.cumsum(lens, out=off[1:])
+        ids, labels = np.ascontiguousarray(ids), np.ascontiguousarray(labels)
         assert len(ids) == len(labels) == off[-1]
         self._check(self.lib.blim_set_texts(self.h, which, ids.ctypes.data_as(ctypes.c_void_p), labels.ctypes.data_as(ctypes.c_void_p),
                                             off.ctypes.data_as(ctypes.c_void_p), len(ids_list)))

@@ -51,7 +51,7 @@ def get_recall(t2v, v2t, t2v_ids=None, v2t_ids=None, engine=None):
     return _pack(out[0], out[1])
 
 
-def fused_rerank(engine, t2v_c, v2t_c, t2v_iv2, v2t_iv2, alpha, c, cpn=True, zero_shot=False):
+def fused_rerank(engine, t2v_c, v2t_c, t2v_iv2, v2t_iv2, alpha, c, cpn=True, zero_shot=False, use_query=True):
     """The "blim" row of val_one_epoch on compact candidate arrays (training_utils.py:154-165 + 173-221).
     Returns (result dict, per-direction dict with fused scores / candidate order / ground-truth ranks, all on device)."""
     full = not zero_shot
@@ -60,7 +60,8 @@ def fused_rerank(engine, t2v_c, v2t_c, t2v_iv2, v2t_iv2, alpha, c, cpn=True, zer
         zero_f64 = zero_shot and d == "t2v"
         fused, order, rank, zero = engine.fuse_rerank(
             comp["idx"], comp.get("candidate_likelihood"), comp.get("candidate_prior") if cpn else None, comp.get("query_likelihood"),
-            iv2, a, cq, ce, use_prior=cpn and "candidate_prior" in comp, use_query=full or d == "t2v", cpn_zero_f64=zero_f64)
+            iv2, a, cq, ce, use_prior=cpn and "candidate_prior" in comp, use_query=use_query and (full or d == "t2v"),
+            cpn_zero_f64=zero_f64)
         detail[d] = {"fused": fused, "order": order, "rank": rank, "zero": zero}
     for d in ("t2v", "v2t"):
         if int(detail[d]["zero"].item()) != 0:
@@ -71,26 +72,39 @@ def fused_rerank(engine, t2v_c, v2t_c, t2v_iv2, v2t_iv2, alpha, c, cpn=True, zer
     return _pack(recalls[0], recalls[1]), detail
 
 
+def _recall_device(engine, t2v_mat, v2t_mat):
+    """get_recall on device-resident dense fp32 matrices (None = the reference's np.zeros placeholder -> recalls 0)."""
+    out = []
+    for m in (t2v_mat, v2t_mat):
+        if m is None:
+            out.append((0.0, 0.0, 0.0))
+            continue
+        rank, zero = engine.rank_dense(m)
+        out.append((0.0, 0.0, 0.0) if int(zero.item()) != 0 else _recall_from_ranks(rank.cpu().numpy(), m.shape[0]))
+    return _pack(out[0], out[1])
+
+
 def val_one_epoch(model, data_loader, optimizer, device, epoch, loss_scaler, tokenizer=None, args=None):
     """Same contract as the reference's val_one_epoch (training_utils.py:140-169): the result table for the rows
-    internvideo2 / candidate_likelihood / query_likelihood / cpn_candidate_likelihood / blim."""
+    internvideo2 / candidate_likelihood / query_likelihood / cpn_candidate_likelihood / blim.  Everything is ranked on
+    the device from the matrices evaluation() left there; nothing is uploaded again."""
     m = _engine_model(model)
     eng = m.engine
     t2v_dict, v2t_dict = evaluation(model, data_loader, device, tokenizer, args)
-    n = len(data_loader.dataset)
     zero_shot = args.resume == "" and args.eval
     full = not zero_shot
-    results = {}
-    zt, zv = np.zeros((n, n)), np.zeros((n, n))
-    for name in ("internvideo2", "candidate_likelihood", "query_likelihood"):
-        results[name] = get_recall(t2v_dict.get(name, zt), v2t_dict.get(name, zv), engine=eng)
-    if args.cpn:
-        cpn_t2v = t2v_dict["candidate_likelihood"] - args.alpha[0] * t2v_dict["candidate_prior"] if full else np.zeros((n, n))
-        cpn_v2t = v2t_dict["candidate_likelihood"] - args.alpha[1] * v2t_dict["candidate_prior"]
-        results["cpn_candidate_likelihood"] = get_recall(cpn_t2v, cpn_v2t, engine=eng)
+    t2v_dev, v2t_dev = m.last_dense
     t2v_c, v2t_c = m.last_compact
-    dev = eng.device
-    results["blim"], m.last_rerank = fused_rerank(eng, t2v_c, v2t_c, torch.from_numpy(t2v_dict["internvideo2"]).to(dev),
-                                                  torch.from_numpy(v2t_dict["internvideo2"]).to(dev), args.alpha, args.c,
+    results = {}
+    for name in ("internvideo2", "candidate_likelihood", "query_likelihood"):
+        results[name] = _recall_device(eng, t2v_dev.get(name), v2t_dev.get(name))
+    if args.cpn:
+        # cand - alpha * prior through the fuse kernel with the ensemble switched off (c = 1: 1*x + 0*iv2 is exact)
+        res, _ = fused_rerank(eng, t2v_c, v2t_c, t2v_dev["internvideo2"], v2t_dev["internvideo2"], args.alpha, (0.0, 0.0, 1.0, 1.0),
+                              cpn=True, zero_shot=False, use_query=False)
+        if not full:   # reference: cpn_t2v = np.zeros -> "matrix absent" -> text->video recalls 0 (tu:154,195)
+            res = _pack((0.0, 0.0, 0.0), (res["v2t_r1"], res["v2t_r5"], res["v2t_r10"]))
+        results["cpn_candidate_likelihood"] = res
+    results["blim"], m.last_rerank = fused_rerank(eng, t2v_c, v2t_c, t2v_dev["internvideo2"], v2t_dev["internvideo2"], args.alpha, args.c,
                                                   cpn=bool(args.cpn), zero_shot=zero_shot)
     return results

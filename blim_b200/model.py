@@ -115,7 +115,14 @@ class BlimModel:
     def ensure_videos(self, video):
         key = ("video", id(video), len(video))
         if self._corpus_keys.get("video") != key:
-            feats = video if torch.is_tensor(video) else torch.stack(list(video), 0)
+            if torch.is_tensor(video):
+                feats = video
+            else:
+                # per-video async H2D copies into one device tensor (no 0.5 GB host-side torch.stack)
+                video = list(video)
+                feats = torch.empty((len(video),) + tuple(video[0].shape), dtype=video[0].dtype, device=self.device)
+                for i, v in enumerate(video):
+                    feats[i].copy_(v, non_blocking=True)
             self.engine.set_videos(feats)
             self._corpus_keys["video"] = key
             self._corpus_keys.pop("vocab", None)

@@ -226,10 +226,9 @@ def evaluation(model, data_loader, device, tokenizer, args):
     full = not zero_shot
 
     # pad-stripped ragged texts go straight to the engine (padding_ids + the mask strip of mvf:333-334 cancel out)
-    strip = lambda xs, ms: [x[mk.bool()] for x, mk in zip(xs, ms)]
     m.ensure_videos(video)
-    eng.set_texts(TEXTS_VTG, strip(vtg_ids, vtg_masks), strip(vtg_labels, vtg_masks))
-    eng.set_texts(TEXTS_TVG, strip(tvg_ids, tvg_masks), strip(tvg_labels, tvg_masks))
+    eng.set_texts(TEXTS_VTG, vtg_ids, vtg_labels, vtg_masks)
+    eng.set_texts(TEXTS_TVG, tvg_ids, tvg_labels, tvg_masks)
     if full:
         m.ensure_vocab(data_loader.dataset.video_vocab, tvg_video_labels)
     m.set_tvg_prefix_length(data_loader.dataset.tvg_prefix_length)      # retrieval_utils.py:210
@@ -238,9 +237,12 @@ def evaluation(model, data_loader, device, tokenizer, args):
     s = score_all(model, plan, cpn=bool(args.cpn), full=full, distributed=bool(getattr(args, "distributed", False)))
     t2v_c, v2t_c = compact_terms(plan, s, cpn=bool(args.cpn), full=full)
     m.last_plan, m.last_compact = plan, (t2v_c, v2t_c)                  # kept on the device for the fused rerank
+    t2v_dev, v2t_dev = dense_matrices(eng, t2v_c, num_texts, num_videos), dense_matrices(eng, v2t_c, num_videos, num_texts)
+    t2v_dev["internvideo2"], v2t_dev["internvideo2"] = t2v_iv2.float().to(eng.device), v2t_iv2.float().to(eng.device)
+    m.last_dense = (t2v_dev, v2t_dev)                                   # device copies: val_one_epoch ranks them in place
 
-    t2v_dict = {k: v.cpu().numpy() for k, v in dense_matrices(eng, t2v_c, num_texts, num_videos).items()}
-    v2t_dict = {k: v.cpu().numpy() for k, v in dense_matrices(eng, v2t_c, num_videos, num_texts).items()}
+    t2v_dict = {k: v.cpu().numpy() for k, v in t2v_dev.items() if k != "internvideo2"}
+    v2t_dict = {k: v.cpu().numpy() for k, v in v2t_dev.items() if k != "internvideo2"}
     t2v_dict["internvideo2"] = t2v_iv2.cpu().numpy()
     v2t_dict["internvideo2"] = v2t_iv2.cpu().numpy()
     print(f"Evaluation time {str(datetime.timedelta(seconds=int(time.time() - start_time)))}")
