@@ -118,9 +118,10 @@ def measured_peaks():
 
 
 def algorithmic_flops(cfg, corpus, plan, cpn=True, full=True):
-    """FLOPs the algorithm needs -- non-padding tokens, every shared prefix once, logits only at scored
-    positions, and in the last layer of a prefix only the QKV projection (KV cache) for all tokens plus the rest of the
-    layer for the one token whose state is read.  Returns (gemm_flops, attention_flops)."""
+    """FLOPs the algorithm needs -- non-padding tokens, every shared prefix once (including the chat-template
+    header shared by all video prefixes / all TVG text prefixes), logits only at scored positions, and in the last layer
+    of a prefix only the QKV projection (KV cache) for all tokens plus the rest of the layer for the one token whose state
+    is read.  Returns (gemm_flops, attention_flops)."""
     H, I, V, MM, L = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size, cfg.mm_hidden_size, cfg.num_layers
     nkv = cfg.num_kv_heads * cfg.head_dim
     p_qkv = 2.0 * H * (H + 2 * nkv)                      # per token, one layer
@@ -139,7 +140,8 @@ def algorithmic_flops(cfg, corpus, plan, cpn=True, full=True):
     g = a = 0.0
     vids = np.unique(uv)
     s_v = pre[0] + n_vis
-    g += len(vids) * (prefix(s_v, 1) + n_vis * 2.0 * (MM * H + H * H))                    # video prefixes + projector
+    r_v = int((corpus.vtg_ids[0] == -200).nonzero()[0])                                   # shared header before the video (root)
+    g += len(vids) * (prefix(s_v - r_v, 1) + n_vis * 2.0 * (MM * H + H * H)) + prefix(r_v, 0)   # video prefixes (header once) + projector
     a += len(vids) * att(s_v, (s_v + 1) / 2)
     suf = cap[ut] - 1                                                                     # decoder tokens per pair
     g += float(suf.sum()) * (p_dec + p_lm) + len(vids) * p_lm
@@ -152,7 +154,8 @@ def algorithmic_flops(cfg, corpus, plan, cpn=True, full=True):
     if full:
         texts = np.unique(ut)
         head = nc * (2.0 * H * MM + 2.0 * MM * corpus.n)
-        g += float(sum(prefix(x, 1) for x in t0[texts])) + len(uv) * ((nc - 1) * p_dec + head)
+        r_t = corpus.tvg_prefix_length                                                    # shared header + instruction (root)
+        g += float(sum(prefix(x - r_t, 1) for x in t0[texts])) + prefix(r_t, 0) + len(uv) * ((nc - 1) * p_dec + head)
         g += len(vids) * n_vis * 2.0 * (MM * H + H * H)                                   # tvg_mlp projector
         a += float(sum(att(x, (x + 1) / 2) for x in t0[texts])) + float(sum(att(nc - 1, t0[t] + nc / 2) for t in ut))
         if cpn:

@@ -34,8 +34,9 @@ struct AttnWorkTc {
   int n_tok;    // tokens in the block (<= 128 / G)
   int a_start;  // prefix key rows [a_start, a_start + a_len) in k_a / v_a
   int a_len;
-  int kb0;      // first own key row needed (= first token of the sequence that contains tok0)
-  int pad0, pad1, pad2;
+  int kb0;      // first own key needed, as a run token index (= first token of the sequence that contains tok0)
+  int b_off;    // own key row of token t = t + b_off (non-zero when a prefix run writes its K/V behind replicated root rows)
+  int pad1, pad2;
 };
 struct AttnParamsTc {
   const __nv_bfloat16* q;
@@ -129,7 +130,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_cons
       own = true;
       key0 = w.kb0 + (c - n_a) * kTcKeys;
       nk = min(kTcKeys, w.tok0 + w.n_tok - key0);
-      tm_row = p.b_row0 + key0;
+      tm_row = p.b_row0 + key0 + w.b_off;
     }
   };
   // one elected thread: TMA a [64 keys x DH] chunk as kSub boxes of 64 columns
@@ -374,7 +375,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
       own = true;
       key0 = w.kb0 + (c - n_a) * kTcKeys;
       nk = min(kTcKeys, w.tok0 + w.n_tok - key0);
-      tm_row = p.b_row0 + key0;
+      tm_row = p.b_row0 + key0 + w.b_off;
     }
   };
   auto stage = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tm_row) {
@@ -580,7 +581,8 @@ inline void build_attn_works_tc(const AttnSeq* seqs, int n_seqs, int group, std:
     int s1 = s0 + 1;
     if (seqs[s0].a_len > 0)
       while (s1 < n_seqs && seqs[s1].a_len == seqs[s0].a_len && seqs[s1].a_start == seqs[s0].a_start &&
-             seqs[s1].q_start == seqs[s1 - 1].q_start + seqs[s1 - 1].q_len)
+             seqs[s1].q_start == seqs[s1 - 1].q_start + seqs[s1 - 1].q_len &&
+             seqs[s1].b_start - seqs[s1].q_start == seqs[s0].b_start - seqs[s0].q_start)
         ++s1;
     for (int s = s0; s < s1; ++s)
       for (int t = 0; t < seqs[s].q_len; ++t) tok_seq_start[seqs[s].q_start + t] = seqs[s].q_start;
@@ -594,7 +596,8 @@ inline void build_attn_works_tc(const AttnSeq* seqs, int n_seqs, int group, std:
       w.a_start = seqs[s0].a_start;
       w.a_len = seqs[s0].a_len;
       w.kb0 = seqs[cur].q_start;
-      w.pad0 = w.pad1 = w.pad2 = 0;
+      w.b_off = seqs[cur].b_start - seqs[cur].q_start;
+      w.pad1 = w.pad2 = 0;
       works.push_back(w);
     }
     s0 = s1;

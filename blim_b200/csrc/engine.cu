@@ -81,22 +81,25 @@ struct TextTable {
 
 // One flat decoder run: T tokens, S sequences.
 struct Run {
-  std::vector<int> tok_src, tok_pos;
+  std::vector<int> tok_src, tok_pos, tok_slot;
   std::vector<uint8_t> key_valid;
   std::vector<AttnSeq> seqs;
   bool any_invalid = false;
+  bool any_slot = false;  // some token's K/V row differs from its run index (prefix runs behind replicated root rows)
   int T() const { return static_cast<int>(tok_src.size()); }
   void clear() {
-    tok_src.clear(); tok_pos.clear(); key_valid.clear(); seqs.clear(); any_invalid = false;
+    tok_src.clear(); tok_pos.clear(); tok_slot.clear(); key_valid.clear(); seqs.clear(); any_invalid = false; any_slot = false;
   }
-  // returns index of the first token
-  int begin_seq(int a_start, int a_len) {
+  // returns index of the first token; b_start = K/V row of the sequence's first token (-1: its run index)
+  int begin_seq(int a_start, int a_len, int b_start = -1) {
     AttnSeq s;
-    s.q_start = T(); s.q_len = 0; s.a_start = a_start; s.a_len = a_len; s.b_start = T();
+    s.q_start = T(); s.q_len = 0; s.a_start = a_start; s.a_len = a_len; s.b_start = b_start < 0 ? T() : b_start;
+    if (s.b_start != s.q_start) any_slot = true;
     seqs.push_back(s);
     return s.q_start;
   }
   void push(int src, int pos, bool valid = true) {
+    tok_slot.push_back(seqs.back().b_start + seqs.back().q_len);
     tok_src.push_back(src); tok_pos.push_back(pos); key_valid.push_back(valid ? 1 : 0);
     if (!valid) any_invalid = true;
     seqs.back().q_len++;
@@ -140,9 +143,10 @@ struct blim_engine {
 
   // workspaces
   DevBuf x, xn, q, attn, k_own, v_own, act, kp, vp, prefix_last, vis, proj_tmp, lm_a, pred, partial, tgt_logit, logp, uniq_scores;
-  DevBuf d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
+  DevBuf d_tok_slot, d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
   bool attn_tc = true;  // tcgen05 attention (BLIM_ATTN=mma selects the mma.sync kernel, tc1 the first tcgen05 kernel)
   int attn_tc_version = 2;
+  bool root_share = true;   // shared prompt-header root for the prefixes (BLIM_ROOT=0 disables)
   bool fuse_norm = false;  // BLIM_FUSE_NORM=1: RMSNorm fused into the GEMMs around it (measured slower than the standalone kernel)
   DevBuf ssq, rstd;
   CUtensorMap tm_kp, tm_vp, tm_kown, tm_vown;  // K / V buffers as TMA tensors (tcgen05 attention)
@@ -211,13 +215,13 @@ static int gemm(blim_engine* e, const bf16* A, int lda, const bf16* W, int ldw, 
 }
 
 static int gemm_qkv(blim_engine* e, const bf16* A, const LayerW& w, int M, bf16* q_out, bf16* k_out, bf16* v_out, const int* pos,
-                    const float* rstd, cudaStream_t st) {
+                    const int* kv_slot, const float* rstd, cudaStream_t st) {
   if (e->DH == 128) {
-    EpiQkvRope<128>::Params p{q_out, k_out, v_out, w.b_qkv.as<float>(), pos, nullptr, e->rope_cos.as<float>(), e->rope_sin.as<float>(),
+    EpiQkvRope<128>::Params p{q_out, k_out, v_out, w.b_qkv.as<float>(), pos, kv_slot, e->rope_cos.as<float>(), e->rope_sin.as<float>(),
                               e->NQ, e->NKVD, e->rope_n, rstd};
     return gemm<EpiQkvRope<128>>(e, A, e->H, w.w_qkv.as<bf16>(), e->H, M, e->NQKV, e->H, p, st);
   }
-  EpiQkvRope<64>::Params p{q_out, k_out, v_out, w.b_qkv.as<float>(), pos, nullptr, e->rope_cos.as<float>(), e->rope_sin.as<float>(),
+  EpiQkvRope<64>::Params p{q_out, k_out, v_out, w.b_qkv.as<float>(), pos, kv_slot, e->rope_cos.as<float>(), e->rope_sin.as<float>(),
                            e->NQ, e->NKVD, e->rope_n, rstd};
   return gemm<EpiQkvRope<64>>(e, A, e->H, w.w_qkv.as<bf16>(), e->H, M, e->NQKV, e->H, p, st);
 }
@@ -231,7 +235,7 @@ extern "C" void blim_destroy(blim_engine* e) {
   DevBuf* bufs[] = {&e->embed, &e->lm_head, &e->visual_head, &e->norm, &e->rope_cos, &e->rope_sin, &e->feats, &e->vocab, &e->tvg_vis,
                     &e->x, &e->xn, &e->q, &e->attn, &e->k_own, &e->v_own, &e->act, &e->kp, &e->vp, &e->prefix_last, &e->vis,
                     &e->proj_tmp, &e->lm_a, &e->pred, &e->partial, &e->tgt_logit, &e->logp, &e->uniq_scores, &e->d_tok_src,
-                    &e->d_tok_pos, &e->d_key_valid, &e->d_seqs, &e->d_works, &e->d_idx, &e->d_targets, &e->d_row_off, &e->d_map, &e->d_seq_start, &e->ssq, &e->rstd};
+                    &e->d_tok_pos, &e->d_key_valid, &e->d_seqs, &e->d_works, &e->d_idx, &e->d_targets, &e->d_row_off, &e->d_map, &e->d_seq_start, &e->ssq, &e->rstd, &e->d_tok_slot};
   for (DevBuf* b : bufs) b->release();
   for (LayerW& l : e->layers) {
     l.w_qkv.release(); l.w_o.release(); l.w_gu.release(); l.w_down.release(); l.b_qkv.release(); l.ln1.release(); l.ln2.release();
@@ -273,6 +277,8 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
     const char* a = getenv("BLIM_ATTN");
     e->attn_tc = !(a && std::string(a) == "mma");
     e->attn_tc_version = (a && std::string(a) == "tc1") ? 1 : 2;
+    const char* rs = getenv("BLIM_ROOT");
+    e->root_share = !(rs && std::string(rs) == "0");
     const char* f = getenv("BLIM_FUSE_NORM");
     e->fuse_norm = f && std::string(f) == "1";
   }
@@ -299,7 +305,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
       {&e->lm_a, T * e->H * 2}, {&e->pred, T * e->MM * 2}, {&e->tgt_logit, T * 4}, {&e->logp, T * 4},
       {&e->d_tok_src, T * 4}, {&e->d_tok_pos, T * 4}, {&e->d_key_valid, T}, {&e->d_seqs, T * sizeof(AttnSeq)},
       {&e->d_works, (T * e->G / kAttnRows + T + 1) * sizeof(AttnWorkTc)}, {&e->d_idx, T * 4}, {&e->d_targets, T * 4},
-      {&e->d_row_off, (T + 1) * 4}, {&e->d_seq_start, T * 4}, {&e->ssq, T * 2 * static_cast<size_t>((e->H + kBN - 1) / kBN) * 4}, {&e->rstd, T * 4}};
+      {&e->d_row_off, (T + 1) * 4}, {&e->d_seq_start, T * 4}, {&e->ssq, T * 2 * static_cast<size_t>((e->H + kBN - 1) / kBN) * 4}, {&e->rstd, T * 4}, {&e->d_tok_slot, T * 4}};
   for (auto& a : allocs) {
     cudaError_t r = a.b->reserve(a.bytes);
     if (r != cudaSuccess) {
@@ -594,6 +600,13 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
     CKR(upload(e, e->d_seqs, run.seqs.data(), run.seqs.size() * sizeof(AttnSeq), st));
   }
   CKR(upload(e, e->d_tok_pos, run.tok_pos.data(), T * sizeof(int), st));
+  if (run.any_slot) {
+    if (!to_prefix_cache) return e->fail("internal: K/V slots are only remapped in prefix runs");
+    for (int sl : run.tok_slot)
+      if (sl < 0 || sl >= e->Pmax) return e->fail("internal: K/V slot outside the prefix cache");
+    CKR(upload(e, e->d_tok_slot, run.tok_slot.data(), T * sizeof(int), st));
+  }
+  const int* kv_slot = run.any_slot ? e->d_tok_slot.as<int>() : nullptr;
   if (run.any_invalid) CKR(upload(e, e->d_key_valid, run.key_valid.data(), T, st));
   if (!assembled) {
     CKR(upload(e, e->d_tok_src, run.tok_src.data(), T * sizeof(int), st));
@@ -628,7 +641,7 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
     bf16* k_out = to_prefix_cache ? kpl : e->k_own.as<bf16>();
     bf16* v_out = to_prefix_cache ? vpl : e->v_own.as<bf16>();
     if (!fuse) CKR(rmsnorm(e, e->xn.as<bf16>(), e->x.as<float>(), nullptr, nullptr, w.ln1.as<float>(), T, st));
-    CKR(gemm_qkv(e, e->xn.as<bf16>(), w, T, e->q.as<bf16>(), k_out, v_out, e->d_tok_pos.as<int>(), rstd, st));
+    CKR(gemm_qkv(e, e->xn.as<bf16>(), w, T, e->q.as<bf16>(), k_out, v_out, e->d_tok_pos.as<int>(), kv_slot, rstd, st));
     const bool prune = last_rows != nullptr && l == e->NL - 1;
     if (prune && last_rows->empty()) break;
     const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(e->DH));
@@ -714,10 +727,11 @@ struct BatchUnit {
 };
 
 static int plan_batches(blim_engine* e, const std::vector<UnitPlan>& units, const std::vector<Item>& items, int max_items,
-                        std::vector<std::vector<BatchUnit>>& batches) {
+                        std::vector<std::vector<BatchUnit>>& batches, int reserve_rows = 0) {
   batches.clear();
   std::vector<BatchUnit> cur;
-  const int pcap_hard = std::min(e->Pmax, e->Tmax);  // a prefix run is also one decoder run
+  const int pcap_hard = std::min(e->Pmax, e->Tmax) - reserve_rows;  // a prefix run is also one decoder run; root rows come first
+  if (pcap_hard <= 0) return e->fail("workspace too small for the shared prompt header");
   // balance: n batches of roughly equal size instead of (n-1) full ones and a small tail (small runs waste the GEMMs)
   long long tot_p = 0, tot_s = 0, tot_i = 0;
   int max_p = 0, max_s = 0;
@@ -775,6 +789,28 @@ static int ensure_tvg_vis(blim_engine* e, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ shared prompt root
+// The first R tokens of every prefix of a batch are often the same chat-template header at the same positions; being
+// causal, their K/V rows are identical for all units.  They are prefilled ONCE into cache rows [0, R) (a run that only
+// fills the KV cache) and copied in front of every unit's own rows, so a unit's cached prefix stays one contiguous
+// segment [root copy | unit tokens] for the cascade attention of the suffix run.
+static int prefill_root(blim_engine* e, const int32_t* ids, int R, const std::vector<int>& unit_bases, cudaStream_t st) {
+  Run rr;
+  rr.begin_seq(0, 0);
+  for (int j = 0; j < R; ++j) rr.push(ids[j], j);
+  rr.end_seq();
+  const std::vector<int> none;
+  CKR(run_decoder(e, rr, true, false, st, &none));
+  const int U = static_cast<int>(unit_bases.size());
+  if (U == 0) return 0;
+  CKR(upload(e, e->d_idx, unit_bases.data(), U * sizeof(int), st));
+  dim3 grid(static_cast<unsigned>(U), static_cast<unsigned>(e->NL), 2);
+  replicate_root_rows_kernel<<<grid, 128, 0, st>>>(e->kp.as<bf16>(), e->vp.as<bf16>(), e->d_idx.as<int>(), R, e->NKVD,
+                                                   static_cast<size_t>(e->Pmax) * e->NKVD);
+  CKL();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ scoring: VTG / VTG prior
 static int score_vtg(blim_engine* e, bool prior, const std::vector<std::pair<int, int>>& keys /* (v, t) unique */, float* out_unique,
                      cudaStream_t st) {
@@ -804,8 +840,14 @@ static int score_vtg(blim_engine* e, bool prior, const std::vector<std::pair<int
     items[i].key = static_cast<int>(i);
     units[it->second].items.push_back(static_cast<int>(i));
   }
+  // root sharing (likelihood only: the prior's prefix is a single 26-token sequence anyway); needs the kernels that
+  // understand remapped K/V rows
+  const bool root_enabled = !prior && e->root_share;
+  int max_root = 0;
+  if (root_enabled)
+    for (const PromptGroup& g : tt.groups) max_root = std::max(max_root, static_cast<int>(g.pre.size()));
   std::vector<std::vector<BatchUnit>> batches;
-  CKR(plan_batches(e, units, items, e->Tmax / 2, batches));
+  CKR(plan_batches(e, units, items, e->Tmax / 2, batches, max_root));
 
   Run run;
   for (const auto& batch : batches) {
@@ -829,14 +871,37 @@ static int score_vtg(blim_engine* e, bool prior, const std::vector<std::pair<int
         it = nx;
       }
     }
-    // ---- prefix run
-    run.clear();
+    // ---- prefix run.  With a shared root (all units of the batch use the same prompt group) the header tokens are
+    //      prefilled once and only [visual rows | prompt tail] run per video.
+    int R = 0;
+    if (root_enabled) {
+      const int g0 = unit_key[batch[0].unit].second;
+      bool same = true;
+      for (const BatchUnit& bu : batch) same = same && unit_key[bu.unit].second == g0;
+      if (same) R = static_cast<int>(tt.groups[g0].pre.size());
+    }
     std::vector<int> unit_start(batch.size()), unit_len(batch.size()), last_tok(batch.size());
+    if (R > 0) {
+      int base = R;
+      for (size_t b = 0; b < batch.size(); ++b) {
+        const PromptGroup& g = tt.groups[unit_key[batch[b].unit].second];
+        unit_start[b] = base;
+        unit_len[b] = R + n_vis + static_cast<int>(g.post.size());
+        base += unit_len[b];
+      }
+      CKR(prefill_root(e, tt.groups[unit_key[batch[0].unit].second].pre.data(), R, unit_start, st));
+    }
+    run.clear();
     for (size_t b = 0; b < batch.size(); ++b) {
       const PromptGroup& g = tt.groups[unit_key[batch[b].unit].second];
-      unit_start[b] = run.begin_seq(0, 0);
       int pos = 0;
-      for (int32_t id : g.pre) run.push(id, pos++);
+      if (R > 0) {
+        run.begin_seq(unit_start[b], R, unit_start[b] + R);   // attends to its root copy, writes K/V right behind it
+        pos = R;
+      } else {
+        unit_start[b] = run.begin_seq(0, 0);
+        for (int32_t id : g.pre) run.push(id, pos++);
+      }
       if (!prior) {
         const int r0 = vis_row0[unit_key[batch[b].unit].first];
         for (int j = 0; j < n_vis; ++j) run.push(-1 - (r0 + j), pos++);
@@ -845,7 +910,7 @@ static int score_vtg(blim_engine* e, bool prior, const std::vector<std::pair<int
       }
       for (int32_t id : g.post) run.push(id, pos++);
       run.end_seq();
-      unit_len[b] = run.T() - unit_start[b];
+      if (R == 0) unit_len[b] = run.T() - unit_start[b];
       last_tok[b] = run.T() - 1;
     }
     CKR(run_decoder(e, run, true, false, st, &last_tok));
@@ -955,23 +1020,48 @@ static int score_tvg(blim_engine* e, bool prior, const std::vector<std::pair<int
     items[i].key = static_cast<int>(i);
     units[u].items.push_back(static_cast<int>(i));
   }
+  const bool root_enabled = !prior && e->root_share && e->tvg_prefix_len > 0;
   std::vector<std::vector<BatchUnit>> batches;
-  CKR(plan_batches(e, units, items, e->Tmax / std::max(1, NC), batches));
+  CKR(plan_batches(e, units, items, e->Tmax / std::max(1, NC), batches, root_enabled ? e->tvg_prefix_len : 0));
 
   Run run;
   const float scale = 1.0f / sqrtf(static_cast<float>(e->MM));
   for (const auto& batch : batches) {
-    // ---- prefix run (text tokens only, embeddings)
-    run.clear();
+    // ---- prefix run (text tokens only, embeddings).  Likelihood: the first tvg_prefix_length tokens (system / user
+    //      header + instruction) are the same for every text -> shared root, prefilled once per batch.
+    int R = 0;
+    if (root_enabled) {
+      R = e->tvg_prefix_len;
+      const int t0 = unit_text[batch[0].unit];
+      for (const BatchUnit& bu : batch) {
+        const int t = unit_text[bu.unit];
+        if (unit_plen[bu.unit] <= R || memcmp(&tt.ids[tt.off[t]], &tt.ids[tt.off[t0]], R * sizeof(int32_t)) != 0) { R = 0; break; }
+      }
+    }
     std::vector<int> unit_start(batch.size()), unit_len(batch.size()), last_tok(batch.size());
+    if (R > 0) {
+      int base = R;
+      for (size_t b = 0; b < batch.size(); ++b) {
+        unit_start[b] = base;
+        unit_len[b] = unit_plen[batch[b].unit];
+        base += unit_len[b];
+      }
+      CKR(prefill_root(e, &tt.ids[tt.off[unit_text[batch[0].unit]]], R, unit_start, st));
+    }
+    run.clear();
     bool any_prefix = false;
     for (size_t b = 0; b < batch.size(); ++b) {
       const int t = unit_text[batch[b].unit];
       const int plen = unit_plen[batch[b].unit];
-      unit_start[b] = run.begin_seq(0, 0);
-      for (int j = 0; j < plen; ++j) run.push(tt.ids[tt.off[t] + j], j);
+      if (R > 0) {
+        run.begin_seq(unit_start[b], R, unit_start[b] + R);
+        for (int j = R; j < plen; ++j) run.push(tt.ids[tt.off[t] + j], j);
+      } else {
+        unit_start[b] = run.begin_seq(0, 0);
+        for (int j = 0; j < plen; ++j) run.push(tt.ids[tt.off[t] + j], j);
+        unit_len[b] = plen;
+      }
       run.end_seq();
-      unit_len[b] = plen;
       last_tok[b] = run.T() - 1;
       any_prefix = any_prefix || plen > 0;
     }

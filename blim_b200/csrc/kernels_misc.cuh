@@ -285,6 +285,18 @@ __global__ void scatter_scores_kernel(float* __restrict__ dense, int n_cols, con
   if (i < n) dense[static_cast<size_t>(row[i]) * n_cols + col[i]] = val[i];
 }
 
+// Replicate the K/V rows [0, n_rows) of every layer of the prefix cache to rows [dst[u], dst[u] + n_rows) for every unit u:
+// the shared "root" of the prefixes (chat-template header) is prefilled once and copied in front of each unit's own rows.
+// grid = (n_units, n_layers, 2 [K, V]); w = row width in elements (w % 8 == 0).
+__global__ void replicate_root_rows_kernel(__nv_bfloat16* __restrict__ kp, __nv_bfloat16* __restrict__ vp, const int* __restrict__ dst,
+                                           int n_rows, int w, size_t layer_stride) {
+  __nv_bfloat16* base = (blockIdx.z == 0 ? kp : vp) + static_cast<size_t>(blockIdx.y) * layer_stride;
+  const __nv_bfloat16* src = base;
+  __nv_bfloat16* out = base + static_cast<size_t>(dst[blockIdx.x]) * w;
+  const int n = n_rows * (w / 8);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(src)[i];
+}
+
 // ------------------------------------------------------------------------------------------------ stage-1 candidates
 // Per-row top-k of the InternVideo2 similarity rows (reference: sims.topk(k), retrieval_utils.py:52,117): one warp per row,
 // k rounds of a warp arg-max over the row staged in shared memory (ties: lowest column first), results in descending order.
