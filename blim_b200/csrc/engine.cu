@@ -146,6 +146,9 @@ struct blim_engine {
   DevBuf d_tok_slot, d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
   bool attn_tc = true;  // tcgen05 attention (BLIM_ATTN=mma selects the mma.sync kernel, tc1 the first tcgen05 kernel)
   int attn_tc_version = 2;
+  uint8_t* arena = nullptr;  // pinned staging arena for scheduler metadata (see upload())
+  size_t arena_cap = 0, arena_off = 0;
+  bool arena_disabled = false;
   bool root_share = true;   // shared prompt-header root for the prefixes (BLIM_ROOT=0 disables)
   bool fuse_norm = false;  // BLIM_FUSE_NORM=1: RMSNorm fused into the GEMMs around it (measured slower than the standalone kernel)
   DevBuf ssq, rstd;
@@ -241,6 +244,7 @@ extern "C" void blim_destroy(blim_engine* e) {
     l.w_qkv.release(); l.w_o.release(); l.w_gu.release(); l.w_down.release(); l.b_qkv.release(); l.ln1.release(); l.ln2.release();
   }
   for (ProjW& p : e->proj) { p.w0.release(); p.b0.release(); p.w2.release(); p.b2.release(); }
+  if (e->arena) cudaFreeHost(e->arena);
   for (auto& t : e->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
   delete e;
@@ -544,10 +548,37 @@ static int check_ready(blim_engine* e) {
   return 0;
 }
 
+// Host -> device copy of scheduler metadata.  A cudaMemcpyAsync from pageable memory synchronises the stream before it
+// starts, which would serialise the host-side planning of run k+1 with the GPU execution of run k; the data is therefore
+// staged through a pinned bump arena (truly asynchronous copies).  The arena wraps with one stream synchronisation
+// every ~64 MB of metadata (a run uploads well under 1 MB).
 static int upload(blim_engine* e, DevBuf& dst, const void* src, size_t bytes, cudaStream_t st) {
   if (bytes == 0) return 0;
   CKE(dst.reserve(bytes));
-  CKE(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, st));  // pageable source: staged before return
+  if (!e->arena && !e->arena_disabled) {
+    const char* pe = getenv("BLIM_PINNED");
+    if (pe && std::string(pe) == "0") e->arena_disabled = true;
+  }
+  if (!e->arena && !e->arena_disabled) {
+    e->arena_cap = 64u << 20;
+    if (cudaMallocHost(reinterpret_cast<void**>(&e->arena), e->arena_cap) != cudaSuccess) {
+      e->arena = nullptr;
+      e->arena_cap = 0;
+      cudaGetLastError();
+    }
+  }
+  const size_t need = (bytes + 255) & ~static_cast<size_t>(255);
+  if (need > e->arena_cap) {
+    CKE(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, st));  // pageable source: staged before return
+    return 0;
+  }
+  if (e->arena_off + need > e->arena_cap) {
+    CKE(cudaStreamSynchronize(st));  // every earlier staged copy has been consumed
+    e->arena_off = 0;
+  }
+  memcpy(e->arena + e->arena_off, src, bytes);
+  CKE(cudaMemcpyAsync(dst.p, e->arena + e->arena_off, bytes, cudaMemcpyHostToDevice, st));
+  e->arena_off += need;
   return 0;
 }
 

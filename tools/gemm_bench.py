@@ -15,7 +15,8 @@ def main():
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     shapes = [(8192, 4608, 3584, 0), (8192, 3584, 3584, 0), (8192, 37888, 3584, 5), (8192, 3584, 18944, 0), (16384, 37888, 3584, 5),
               (4096, 152064, 3584, 6), (8192, 8192, 8192, 0), (27072, 3584, 18944, 4), (27072, 3584, 18944, 7), (27072, 3584, 3584, 4),
-              (27072, 3584, 3584, 7), (27072, 3584, 18944, 4), (27072, 3584, 18944, 7)]
+              (27072, 3584, 3584, 7), (27072, 3584, 18944, 4), (27072, 3584, 18944, 7), (27072, 3584, 3584, 0), (27072, 3584, 3584, 3),
+              (27072, 4608, 3584, 0), (27072, 3584, 3584, 4), (27136, 3584, 3584, 0), (18944, 3584, 3584, 0)]
     out = []
     for M, N, K, epi in shapes:
         A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
