@@ -45,6 +45,7 @@ SIGNATURES = {
     "blim_set_videos": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "blim_set_texts": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int]),
     "blim_set_video_vocab": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "blim_build_video_vocab": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "blim_set_tvg_prefix_length": (c_int, [c_void_p, c_int]),
     "blim_score_pairs": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "blim_forward_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),

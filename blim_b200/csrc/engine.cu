@@ -520,6 +520,26 @@ extern "C" int blim_set_video_vocab(blim_engine* e, const void* vocab_dev, int d
   return 0;
 }
 
+// video_vocab computed on the device from the features given to blim_set_videos (no host-side mean / upload).
+extern "C" int blim_build_video_vocab(blim_engine* e, const int32_t* labels, int n_videos, int n_vocab, void* stream) {
+  if (!e || !labels || n_vocab <= 0) return e ? e->fail("bad vocab arguments") : 1;
+  if (e->n_videos <= 0 || n_videos != e->n_videos) return e->fail("blim_build_video_vocab: call blim_set_videos first (same number of videos)");
+  for (int v = 0; v < n_videos; ++v)
+    if (labels[v] < 0 || labels[v] >= n_vocab) return e->fail("video label out of range");
+  CKE(cudaSetDevice(e->device));
+  cudaStream_t st = S(stream);
+  const size_t n = static_cast<size_t>(n_vocab) * e->n_clips * e->MM;
+  CKE(e->vocab.reserve(n * 2));
+  CKE(cudaMemsetAsync(e->vocab.p, 0, n * 2, st));
+  CKR(upload(e, e->d_map, labels, static_cast<size_t>(n_videos) * sizeof(int), st));
+  vocab_from_feats_kernel<<<n_videos * e->n_clips, 128, 0, st>>>(e->vocab.as<bf16>(), e->feats.as<bf16>(), e->d_map.as<int>(), e->n_clips, e->TPC,
+                                                                 e->MM, n_vocab);
+  CKL();
+  e->n_vocab = n_vocab;
+  e->video_labels.assign(labels, labels + n_videos);
+  return 0;
+}
+
 extern "C" int blim_set_tvg_prefix_length(blim_engine* e, int n) {
   if (!e || n < 0) return e ? e->fail("bad tvg prefix length") : 1;
   e->tvg_prefix_len = n;

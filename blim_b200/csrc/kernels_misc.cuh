@@ -167,6 +167,24 @@ __global__ void mean_rows_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfl
   }
 }
 
+// video_vocab built on the device from the stored features (reference: load_video_feature(vid).mean(1) per video,
+// dataloader/base_dataset.py:33-37): vocab[c][label[v]][:] = mean over the `group` tokens of clip c of video v.
+// grid = (n_videos * n_clips); feats [n_videos * n_clips * group, mm] bf16; vocab [n_clips][n_vocab][mm] bf16.
+__global__ void vocab_from_feats_kernel(__nv_bfloat16* __restrict__ vocab, const __nv_bfloat16* __restrict__ feats,
+                                        const int* __restrict__ labels, int n_clips, int group, int mm, int n_vocab) {
+  const int v = blockIdx.x / n_clips, c = blockIdx.x % n_clips;
+  const __nv_bfloat16* src = feats + static_cast<size_t>(blockIdx.x) * group * mm;
+  __nv_bfloat16* dst = vocab + (static_cast<size_t>(c) * n_vocab + labels[v]) * mm;
+  for (int d = threadIdx.x * 2; d < mm; d += blockDim.x * 2) {
+    float a = 0.f, b = 0.f;
+    for (int g = 0; g < group; ++g) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + static_cast<size_t>(g) * mm + d));
+      a += f.x; b += f.y;
+    }
+    *reinterpret_cast<__nv_bfloat162*>(dst + d) = __floats2bfloat162_rn(a / group, b / group);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ log-softmax reductions
 // Merge the per-half-tile (max, sumexp) partials of EpiLse: logp[r] = tgt_logit[r] - (m + log(sum)).
 __global__ void lse_finalize_kernel(float* __restrict__ logp, const float2* __restrict__ partial, const float* __restrict__ tgt_logit,

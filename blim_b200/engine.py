@@ -188,6 +188,13 @@ class Engine:
                                                       labels.ctypes.data_as(ctypes.c_void_p), len(labels), self._stream()))
             torch.cuda.synchronize(self.device)
 
+    def build_video_vocab(self, video_labels, n_vocab=None):
+        """video_vocab on the device from the features of set_videos (base_dataset.py:33-37)."""
+        labels = np.ascontiguousarray(np.asarray(video_labels, dtype=np.int32))
+        n_vocab = int(n_vocab if n_vocab is not None else labels.max() + 1)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.blim_build_video_vocab(self.h, labels.ctypes.data_as(ctypes.c_void_p), len(labels), n_vocab, self._stream()))
+
     def set_tvg_prefix_length(self, n):
         self._check(self.lib.blim_set_tvg_prefix_length(self.h, int(n)))
 

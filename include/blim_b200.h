@@ -79,6 +79,9 @@ int blim_set_videos(blim_engine* e, const void* feats_dev, int dtype, int n_vide
 int blim_set_texts(blim_engine* e, int which, const int32_t* ids_host, const int32_t* labels_host, const int64_t* offsets_host, int n_texts);
 int blim_set_video_vocab(blim_engine* e, const void* vocab_dev, int dtype, int n_vocab, const int32_t* video_labels_host, int n_videos,
                          void* stream);
+/* video_vocab built on the device from the features of blim_set_videos: vocab[label[v]] = features[v].mean(tokens)
+ * (get_video_vocab, dataloader/base_dataset.py:33-37) -- no host-side mean, no vocab upload. */
+int blim_build_video_vocab(blim_engine* e, const int32_t* video_labels_host, int n_videos, int n_vocab, void* stream);
 int blim_set_tvg_prefix_length(blim_engine* e, int n); /* set_tvg_prefix_length, modeling_videochat_flash.py:592 */
 
 /* Score n_pairs (video, text) pairs of one kind; pair_v / pair_t are host arrays, out_scores_dev[n_pairs] is device fp32.

@@ -224,3 +224,15 @@ def test_topk_rows_matches_torch():
         assert eng.topk_rows(m, 4)[0].tolist() == [[1, 2, 4, 3]]
     finally:
         eng.close()
+
+
+def test_device_built_video_vocab_matches_uploaded(golden_case):
+    """blim_build_video_vocab (mean over the 64 tokens on the device) gives the same TVG scores as the uploaded vocab."""
+    name, spec, cfg, weights, corpus, eng, gold = golden_case
+    ref = gold["t2v_tvg_lik"]
+    rows, cols = np.nonzero(ref != -100.0)
+    a = eng.score_pairs(TVG, cols, rows).cpu().numpy()
+    eng.build_video_vocab(corpus.tvg_video_labels.numpy())
+    b = eng.score_pairs(TVG, cols, rows).cpu().numpy()
+    assert np.array_equal(a, b)
+    eng.set_video_vocab(corpus.video_vocab, corpus.tvg_video_labels.numpy())
