@@ -439,6 +439,7 @@ extern "C" int blim_set_rope(blim_engine* e, const float* cos_dev, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------ corpus
+static int upload(blim_engine* e, DevBuf& dst, const void* src, size_t bytes, cudaStream_t st);
 extern "C" int blim_set_videos(blim_engine* e, const void* feats_dev, int dtype, int n_videos, int n_clips, void* stream) {
   if (!e || !feats_dev || n_videos <= 0 || n_clips <= 0) return e ? e->fail("bad video arguments") : 1;
   CKE(cudaSetDevice(e->device));
