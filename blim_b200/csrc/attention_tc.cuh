@@ -569,6 +569,276 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   if (warp == 0) tmem_dealloc<1>(tmem, kTcTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------ v3: S and K double-buffered
+// Same as v2, plus: two S accumulators in TMEM and two K stages in shared memory, so S = Q K^T of chunk c+1 is issued at
+// the TOP of round c (its K chunk was prefetched a whole round earlier) and runs under the softmax of chunk c; at the end
+// of a round only Oc = P V is issued.  All bookkeeping lives in dynamic shared memory (no static __shared__) so that two
+// CTAs of 112.6 KB still fit one SM; the host checks the occupancy and falls back to v2 otherwise.
+template <int DH>
+constexpr int attn_tc3_smem_bytes() {
+  // Q (DH/64 x 16 KB) + 2 x K + 2 x V (DH/64 x 8 KB each) + P (16 KB) + max exchange (512 B) + barriers (64 B)
+  return (DH / 64) * 16384 + 4 * (DH / 64) * 8192 + 16384 + 512 + 64;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(kTc2Threads, 2)
+attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_constant__ CUtensorMap tm_va,
+                     const __grid_constant__ CUtensorMap tm_kb, const __grid_constant__ CUtensorMap tm_vb, const AttnParamsTc p) {
+  constexpr int kSub = DH / 64;
+  constexpr uint32_t kChunkBytes = kSub * 8192;
+  constexpr float kGrow = 8.0f;
+  extern __shared__ __align__(1024) uint8_t smem_tc3[];
+  uint8_t* s_q = smem_tc3;
+  uint8_t* s_k = s_q + kSub * 16384;           // two stages
+  uint8_t* s_v = s_k + 2 * kSub * 8192;        // two stages
+  uint8_t* s_p = s_v + 2 * kSub * 8192;
+  __nv_bfloat16* s_mx = reinterpret_cast<__nv_bfloat16*>(s_p + 16384);   // [2][128] row maxima of the two half-row threads
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 16384 + 512);
+  uint64_t* bar_s = bars;        // [2]
+  uint64_t* bar_k = bars + 2;    // [2]
+  uint64_t* bar_v = bars + 4;    // [2]
+  uint64_t* bar_o = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+  const AttnWorkTc w = p.works[blockIdx.x];
+  const int kvh = blockIdx.y;
+  const int G = p.group;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid & 127, half = tid >> 7;
+
+  if (tid == 0) {
+    if (smem_u32(smem_tc3) & 1023u) __trap();   // the swizzled tiles need a 1024-byte aligned base
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_ka);
+    tma_prefetch_desc(&tm_va);
+    tma_prefetch_desc(&tm_kb);
+    tma_prefetch_desc(&tm_vb);
+  }
+  if (warp == 0) tmem_alloc<1>(tmem_slot, kTcTmemCols);
+
+  const int tok_local = r / G, head = r - tok_local * G;
+  const bool row_ok = tok_local < w.n_tok;
+  const int rt = w.tok0 + (row_ok ? tok_local : 0);
+  const int seq_lo = row_ok ? __ldg(p.tok_seq_start + rt) : 0;
+  {
+    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH;
+#pragma unroll
+    for (int cc = 0; cc < DH / 16; ++cc) {
+      const int c = half * (DH / 16) + cc;
+      cp_async16(s_q + (c >> 3) * 16384 + sw128_offset(r, (c & 7) * 8), src + c * 8, row_ok ? 16 : 0);
+    }
+    cp_async_commit();
+  }
+
+  const int n_a = (w.a_len + kTcKeys - 1) / kTcKeys;
+  const int own_len = w.tok0 + w.n_tok - w.kb0;
+  const int n_chunks = n_a + (own_len + kTcKeys - 1) / kTcKeys;
+
+  auto chunk_keys = [&](int c, int& nk, int& key0, bool& own, int& tm_row) {
+    if (c < n_a) {
+      own = false;
+      key0 = c * kTcKeys;
+      nk = min(kTcKeys, w.a_len - key0);
+      tm_row = p.a_row0 + w.a_start + key0;
+    } else {
+      own = true;
+      key0 = w.kb0 + (c - n_a) * kTcKeys;
+      nk = min(kTcKeys, w.tok0 + w.n_tok - key0);
+      tm_row = p.b_row0 + key0 + w.b_off;
+    }
+  };
+  auto stage = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tm_row) {
+    mbar_arrive_expect_tx(bar, kChunkBytes);
+#pragma unroll
+    for (int sub = 0; sub < kSub; ++sub) tma_load_2d(dst + sub * 8192, tm, bar, kvh * DH + sub * 64, tm_row);
+  };
+  auto stage_k = [&](int c) {
+    int nk, key0, row; bool own;
+    chunk_keys(c, nk, key0, own, row);
+    stage(s_k + (c & 1) * kSub * 8192, own ? &tm_kb : &tm_ka, &bar_k[c & 1], row);
+  };
+  auto stage_v = [&](int c) {
+    int nk, key0, row; bool own;
+    chunk_keys(c, nk, key0, own, row);
+    stage(s_v + (c & 1) * kSub * 8192, own ? &tm_vb : &tm_va, &bar_v[c & 1], row);
+  };
+  auto issue_s = [&](int c, uint32_t tmem) {   // S[c & 1] = Q K(c)^T (tid 0 only)
+    int nk, key0, row; bool own;
+    chunk_keys(c, nk, key0, own, row);
+    const int nk16 = (nk + 15) & ~15;
+    mbar_wait(&bar_k[c & 1], static_cast<uint32_t>((c >> 1) & 1));
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16_ex(128, nk16, 0);
+    const uint32_t k_base = smem_u32(s_k) + (c & 1) * kSub * 8192;
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+      const uint64_t da = make_smem_desc_sw128(smem_u32(s_q) + (kk >> 2) * 16384 + (kk & 3) * 32);
+      const uint64_t db = make_smem_desc_sw128(k_base + (kk >> 2) * 8192 + (kk & 3) * 32);
+      umma_bf16<1>(tmem + (c & 1) * 64, da, db, idesc, kk != 0 ? 1u : 0u);
+    }
+    umma_commit(&bar_s[c & 1]);
+  };
+
+  cp_async_wait<0>();
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();   // barriers initialised, TMEM allocated, Q staged
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    stage_k(0);
+    stage_v(0);
+    if (n_chunks > 1) { stage_k(1); stage_v(1); }
+    issue_s(0, tmem);
+  }
+  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  const uint32_t t_o = t_row + 128 + half * (DH / 2);      // this thread's DH/2 O columns (S0: [0,64), S1: [64,128))
+
+  float m_ref = -INFINITY, l_part = 0.f;
+
+  for (int c = 0; c < n_chunks; ++c) {
+    int nk, key0, tm_row_unused; bool own;
+    chunk_keys(c, nk, key0, own, tm_row_unused);
+    const int nk16 = (nk + 15) & ~15;
+
+    mbar_wait(&bar_s[c & 1], static_cast<uint32_t>((c >> 1) & 1));
+    if (tid == 0) {
+      // S(c) is complete: its K stage is free again, and S(c+1) (other accumulator, K prefetched a round ago) can start now
+      if (c + 1 < n_chunks) issue_s(c + 1, tmem);
+      if (c + 2 < n_chunks) stage_k(c + 2);
+    }
+    __syncwarp();
+    tc_fence_after();
+    float sv[32];
+    if (half * 32 < nk16) {   // warp-uniform
+      uint32_t raw[32];
+      tmem_ld32(t_row + (c & 1) * 64 + half * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(raw[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sv[i] = 0.f;
+    }
+    int j_lo = 0, j_hi = nk - 1;
+    if (own) {
+      j_lo = max(0, seq_lo - key0);
+      j_hi = min(nk - 1, rt - key0);
+    }
+    const bool any_vis = j_hi >= j_lo;
+    const unsigned span = any_vis ? static_cast<unsigned>(j_hi - j_lo) : 0u;
+    float cmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int j = half * 32 + i;
+      bool vis = any_vis && static_cast<unsigned>(j - j_lo) <= span;
+      if (own && p.key_valid && vis) vis = p.key_valid[key0 + j] != 0;
+      const float val = vis ? sv[i] : -INFINITY;
+      sv[i] = val;
+      cmax = fmaxf(cmax, val);
+    }
+    s_mx[half * 128 + r] = __float2bfloat16(cmax);   // both threads of the row use the same (bf16-rounded) pair of maxima
+    tc_fence_before();
+    __syncthreads();   // [A]
+    const float cmax_s = fmaxf(__bfloat162float(s_mx[r]), __bfloat162float(s_mx[128 + r])) * p.scale_log2;
+
+    if (c > 0) {
+      mbar_wait(bar_o, static_cast<uint32_t>((c - 1) & 1));
+      if (tid == 0 && c + 1 < n_chunks) stage_v(c + 1);   // its stage was read by chunk c-1
+      __syncwarp();
+      tc_fence_after();
+    }
+    float corr = 1.f;
+    bool grow = false;
+    if (c == 0) {
+      m_ref = cmax_s;
+    } else if (cmax_s > m_ref + kGrow) {
+      grow = true;
+      corr = exp2f(m_ref - cmax_s);
+      m_ref = cmax_s;
+      l_part *= corr;
+    }
+    if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll
+      for (int h = 0; h < DH / 64; ++h) {
+        uint32_t raw[32];
+        tmem_ld32(t_o + h * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
+        tmem_st32(t_o + h * 32, raw);
+      }
+      tmem_st_wait();
+    }
+    const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+    float csum = 0.f;
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p0 = exp2f(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
+        const float p1 = exp2f(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
+        csum += p0 + p1;
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+        pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      if (half * 32 + j8 * 8 < nk16) *reinterpret_cast<uint4*>(s_p + sw128_offset(r, half * 32 + j8 * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    l_part += csum;
+
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();   // [B] P written, O rescaled
+    if (tid == 0) {
+      mbar_wait(&bar_v[c & 1], static_cast<uint32_t>((c >> 1) & 1));
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16_ex(128, DH, 1);
+      const uint32_t v_base = smem_u32(s_v) + (c & 1) * kSub * 8192;
+      for (int kk = 0; kk < nk16 / 16; ++kk) {
+        const uint64_t da = make_smem_desc_sw128(smem_u32(s_p) + kk * 32);
+        const uint64_t db = make_smem_desc_raw(v_base + kk * 2048, 8192, 1024);
+        umma_bf16<1>(tmem + 128, da, db, idesc, (c > 0 || kk != 0) ? 1u : 0u);
+      }
+      umma_commit(bar_o);
+    }
+  }
+
+  // ---- O / l -> bf16   (the P tile is free: reuse it to add the two half-row sums)
+  mbar_wait(bar_o, static_cast<uint32_t>((n_chunks - 1) & 1));
+  __syncwarp();
+  tc_fence_after();
+  float* s_l = reinterpret_cast<float*>(s_p);
+  s_l[half * 128 + r] = l_part;
+  __syncthreads();
+  const float l = s_l[r] + s_l[128 + r];
+  const float inv = l > 0.f ? 1.0f / l : 0.f;
+  __nv_bfloat16* dst = p.o + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH + half * (DH / 2);
+#pragma unroll
+  for (int h = 0; h < DH / 64; ++h) {
+    uint32_t raw[32];
+    tmem_ld32(t_o + h * 32, raw);
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(raw[c8 * 8 + 2 * e]) * inv, __uint_as_float(raw[c8 * 8 + 2 * e + 1]) * inv);
+          pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        *reinterpret_cast<uint4*>(dst + h * 32 + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc<1>(tmem, kTcTmemCols);
+}
+
 // Host: blocks of 128 / G consecutive tokens over every prefix-sharing group of consecutive sequences, plus the
 // per-token "first token of my sequence" table.
 inline void build_attn_works_tc(const AttnSeq* seqs, int n_seqs, int group, std::vector<AttnWorkTc>& works, std::vector<int>& tok_seq_start,
@@ -625,10 +895,32 @@ inline cudaError_t launch_attention_tc2_impl(const AttnTcMaps& m, const AttnPara
   return cudaGetLastError();
 }
 
+// v3 needs two 112.6 KB CTAs per SM; returns cudaErrorLaunchOutOfResources (caller falls back to v2) when they do not fit.
+template <int DH>
+inline cudaError_t launch_attention_tc3_impl(const AttnTcMaps& m, const AttnParamsTc& p, dim3 grid, cudaStream_t stream) {
+  static int state = 0;  // 0 = unknown, 1 = usable, -1 = does not fit twice
+  if (state == 0) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc3_smem_bytes<DH>());
+    int blocks = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, attention_tc3_kernel<DH>, kTc2Threads, attn_tc3_smem_bytes<DH>());
+    if (e != cudaSuccess) cudaGetLastError();
+    state = (e == cudaSuccess && blocks >= 2) ? 1 : -1;
+  }
+  if (state < 0) return cudaErrorLaunchOutOfResources;
+  attention_tc3_kernel<DH><<<grid, kTc2Threads, attn_tc3_smem_bytes<DH>(), stream>>>(m.ka, m.va, m.kb, m.vb, p);
+  return cudaGetLastError();
+}
+
 inline cudaError_t launch_attention_tc(const AttnTcMaps& m, const AttnParamsTc& p, int n_works, int n_kv_heads, int head_dim,
                                        cudaStream_t stream, int version = 2) {
   if (n_works <= 0) return cudaSuccess;
   dim3 grid(static_cast<unsigned>(n_works), static_cast<unsigned>(n_kv_heads));
+  if (version == 3) {
+    cudaError_t e = head_dim == 128 ? launch_attention_tc3_impl<128>(m, p, grid, stream)
+                  : head_dim == 64 ? launch_attention_tc3_impl<64>(m, p, grid, stream) : cudaErrorInvalidValue;
+    if (e != cudaErrorLaunchOutOfResources) return e;
+    version = 2;  // two CTAs per SM do not fit: the single-buffered kernel is the better choice
+  }
   if (version == 2) {
     if (head_dim == 128) return launch_attention_tc2_impl<128>(m, p, grid, stream);
     if (head_dim == 64) return launch_attention_tc2_impl<64>(m, p, grid, stream);
