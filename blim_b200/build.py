@@ -16,7 +16,7 @@ LIB = os.path.join(CSRC, "libblim_b200.so")
 STAMP = os.path.join(CSRC, ".build_stamp")
 
 SOURCES = ["engine.cu"]
-HEADERS = ["ptx_sm100.cuh", "gemm_sm100.cuh", "attention.cuh", "kernels_misc.cuh", os.path.join(ROOT, "include", "blim_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join(ROOT, "include", "blim_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -19,6 +19,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -905,6 +907,8 @@ inline cudaError_t launch_attention_tc3_impl(const AttnTcMaps& m, const AttnPara
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, attention_tc3_kernel<DH>, kTc2Threads, attn_tc3_smem_bytes<DH>());
     if (e != cudaSuccess) cudaGetLastError();
     state = (e == cudaSuccess && blocks >= 2) ? 1 : -1;
+    if (getenv("BLIM_DEBUG")) fprintf(stderr, "[blim] attention v3 (head_dim %d): %d CTA(s) per SM with %d B dynamic smem -> %s\n", DH, blocks,
+                                      attn_tc3_smem_bytes<DH>(), state > 0 ? "used" : "falling back to v2");
   }
   if (state < 0) return cudaErrorLaunchOutOfResources;
   attention_tc3_kernel<DH><<<grid, kTc2Threads, attn_tc3_smem_bytes<DH>(), stream>>>(m.ka, m.va, m.kb, m.vb, p);
