@@ -903,6 +903,7 @@ inline cudaError_t launch_attention_tc3_impl(const AttnTcMaps& m, const AttnPara
   static int state = 0;  // 0 = unknown, 1 = usable, -1 = does not fit twice
   if (state == 0) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc3_smem_bytes<DH>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc3_kernel<DH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int blocks = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, attention_tc3_kernel<DH>, kTc2Threads, attn_tc3_smem_bytes<DH>());
     if (e != cudaSuccess) cudaGetLastError();
