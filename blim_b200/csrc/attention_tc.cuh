@@ -22,6 +22,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "attention.cuh"
@@ -904,9 +905,21 @@ inline cudaError_t launch_attention_tc3_impl(const AttnTcMaps& m, const AttnPara
   if (state == 0) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc3_smem_bytes<DH>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc3_kernel<DH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    int blocks = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, attention_tc3_kernel<DH>, kTc2Threads, attn_tc3_smem_bytes<DH>());
-    if (e != cudaSuccess) cudaGetLastError();
+    // two CTAs per SM?  (the occupancy API under-reports with large dynamic shared memory, so the two limits are checked
+    // directly: 228 KB of shared memory per SM incl. 1 KB reserved per CTA, 64 K registers allocated in units of 8 per thread)
+    cudaFuncAttributes fa;
+    int blocks = 0, dev = 0, smem_sm = 0, regs_sm = 0;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, attention_tc3_kernel<DH>);
+    if (e == cudaSuccess) e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+    if (e == cudaSuccess) {
+      const int smem_cta = ((attn_tc3_smem_bytes<DH>() + static_cast<int>(fa.sharedSizeBytes) + 127) & ~127) + 1024;
+      const int regs_cta = kTc2Threads * ((fa.numRegs + 7) & ~7);
+      blocks = std::min(smem_sm / smem_cta, regs_sm / regs_cta);
+    } else {
+      cudaGetLastError();
+    }
     state = (e == cudaSuccess && blocks >= 2) ? 1 : -1;
     if (getenv("BLIM_DEBUG")) fprintf(stderr, "[blim] attention v3 (head_dim %d): %d CTA(s) per SM with %d B dynamic smem -> %s\n", DH, blocks,
                                       attn_tc3_smem_bytes<DH>(), state > 0 ? "used" : "falling back to v2");
