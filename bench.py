@@ -335,6 +335,7 @@ def main():
     sampler.start()
     total_ms, (res, plan) = timed(step_device, args.steps)
     clocks = sampler.stop()
+    detail = eng.profile_read_detail()
     prof = eng.profile_read()
     eng.profile(False)
     launches = (eng.kernel_launches() - launches0) // max(1, args.steps)
@@ -356,7 +357,12 @@ def main():
                 "executed_gemm_flops_per_step": executed_flops, "gemm_launches_per_step": prof["gemm_launches"] // max(1, args.steps),
                 "gemm_ms_per_step": prof["gemm_ms"] / args.steps, "attention_ms_per_step": prof["attn_ms"] / args.steps,
                 "gemm_share_of_step": prof["gemm_ms"] / total_ms, "attention_share_of_step": prof["attn_ms"] / total_ms,
-                "whole_step_tflops": (f_gemm + f_attn) * share / (ms_per_step / 1000.0) / 1e12}
+                "whole_step_tflops": (f_gemm + f_attn) * share / (ms_per_step / 1000.0) / 1e12,
+                # per-kind device time (CUDA events on the launching stream, this rank); TFLOP/s = EXECUTED 2*M*N*K / time
+                "by_kernel": {k: {"ms_per_step": d["ms"] / args.steps, "launches_per_step": d["launches"] // max(1, args.steps),
+                                  "share_of_step": d["ms"] / total_ms,
+                                  "tflops": (d["flops"] / (d["ms"] / 1000.0) / 1e12) if d["flops"] > 0 and d["ms"] > 0 else None}
+                              for k, d in detail.items()}}
 
     # end to end through the reference-facing API with HOST inputs (pinned), copies inside the timed region
     e2e = None

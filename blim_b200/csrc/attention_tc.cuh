@@ -234,8 +234,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_cons
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p0 = exp2f(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
-          const float p1 = exp2f(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
+          const float p0 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
+          const float p1 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
           csum += p0 + p1;
           __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
           pk[e] = *reinterpret_cast<uint32_t*>(&b2);
@@ -450,22 +450,31 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
 #pragma unroll
       for (int i = 0; i < 32; ++i) sv[i] = 0.f;
     }
-    int j_lo = 0, j_hi = nk - 1;
-    if (own) {
-      j_lo = max(0, seq_lo - key0);
-      j_hi = min(nk - 1, rt - key0);
-    }
-    const bool any_vis = j_hi >= j_lo;
-    const unsigned span = any_vis ? static_cast<unsigned>(j_hi - j_lo) : 0u;
     float cmax = -INFINITY;
+    if (!own && nk == kTcKeys) {   // CTA-uniform fast path: a full chunk of the shared prefix, every key visible
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int j = half * 32 + i;
-      bool vis = any_vis && static_cast<unsigned>(j - j_lo) <= span;
-      if (own && p.key_valid && vis) vis = p.key_valid[key0 + j] != 0;
-      const float val = vis ? sv[i] : -INFINITY;
-      sv[i] = val;
-      cmax = fmaxf(cmax, val);
+      for (int i = 0; i < 32; ++i) cmax = fmaxf(cmax, sv[i]);
+    } else {
+      int j_lo = 0, j_hi = nk - 1;
+      if (own) {
+        j_lo = max(0, seq_lo - key0);
+        j_hi = min(nk - 1, rt - key0);
+      }
+      // visible keys among this thread's 32 as a bit mask: [j_lo, j_hi] clipped to the half's window
+      const int lo = max(j_lo - half * 32, 0), hi = min(j_hi - half * 32, 31);
+      uint32_t vmask = (hi >= lo) ? ((0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo)) : 0u;
+      if (own && p.key_valid != nullptr && vmask != 0u) {
+        const uint8_t* kv = p.key_valid + key0 + half * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (((vmask >> i) & 1u) && kv[i] == 0) vmask &= ~(1u << i);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float val = ((vmask >> i) & 1u) ? sv[i] : -INFINITY;
+        sv[i] = val;
+        cmax = fmaxf(cmax, val);
+      }
     }
     s_x[half][r] = cmax;
     tc_fence_before();
@@ -511,8 +520,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
       uint32_t pk[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float p0 = exp2f(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
-        const float p1 = exp2f(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
+        const float p0 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
+        const float p1 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
         csum += p0 + p1;
         __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
         pk[e] = *reinterpret_cast<uint32_t*>(&b2);
@@ -724,22 +733,31 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
 #pragma unroll
       for (int i = 0; i < 32; ++i) sv[i] = 0.f;
     }
-    int j_lo = 0, j_hi = nk - 1;
-    if (own) {
-      j_lo = max(0, seq_lo - key0);
-      j_hi = min(nk - 1, rt - key0);
-    }
-    const bool any_vis = j_hi >= j_lo;
-    const unsigned span = any_vis ? static_cast<unsigned>(j_hi - j_lo) : 0u;
     float cmax = -INFINITY;
+    if (!own && nk == kTcKeys) {   // CTA-uniform fast path: a full chunk of the shared prefix, every key visible
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int j = half * 32 + i;
-      bool vis = any_vis && static_cast<unsigned>(j - j_lo) <= span;
-      if (own && p.key_valid && vis) vis = p.key_valid[key0 + j] != 0;
-      const float val = vis ? sv[i] : -INFINITY;
-      sv[i] = val;
-      cmax = fmaxf(cmax, val);
+      for (int i = 0; i < 32; ++i) cmax = fmaxf(cmax, sv[i]);
+    } else {
+      int j_lo = 0, j_hi = nk - 1;
+      if (own) {
+        j_lo = max(0, seq_lo - key0);
+        j_hi = min(nk - 1, rt - key0);
+      }
+      // visible keys among this thread's 32 as a bit mask: [j_lo, j_hi] clipped to the half's window
+      const int lo = max(j_lo - half * 32, 0), hi = min(j_hi - half * 32, 31);
+      uint32_t vmask = (hi >= lo) ? ((0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo)) : 0u;
+      if (own && p.key_valid != nullptr && vmask != 0u) {
+        const uint8_t* kv = p.key_valid + key0 + half * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (((vmask >> i) & 1u) && kv[i] == 0) vmask &= ~(1u << i);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float val = ((vmask >> i) & 1u) ? sv[i] : -INFINITY;
+        sv[i] = val;
+        cmax = fmaxf(cmax, val);
+      }
     }
     s_mx[half * 128 + r] = __float2bfloat16(cmax);   // both threads of the row use the same (bf16-rounded) pair of maxima
     tc_fence_before();
@@ -781,8 +799,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
       uint32_t pk[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float p0 = exp2f(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
-        const float p1 = exp2f(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
+        const float p0 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
+        const float p1 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
         csum += p0 + p1;
         __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
         pk[e] = *reinterpret_cast<uint32_t*>(&b2);

@@ -157,16 +157,16 @@ struct blim_engine {
 
   // optional per-launch device timing (bench.py roofline): CUDA events around every GEMM / attention launch
   bool profiling = false;
-  struct Timed { cudaEvent_t a, b; int cat; };
+  struct Timed { cudaEvent_t a, b; int cat; int sub; double flops; };
   std::vector<Timed> timed;
   std::vector<cudaEvent_t> event_pool;
   cudaEvent_t get_event() {
     if (!event_pool.empty()) { cudaEvent_t ev = event_pool.back(); event_pool.pop_back(); return ev; }
     cudaEvent_t ev; cudaEventCreate(&ev); return ev;
   }
-  void tic(int cat, cudaStream_t st) {
+  void tic(int cat, cudaStream_t st, int sub = 0, double flops = 0.0) {
     if (!profiling) return;
-    Timed t; t.a = get_event(); t.b = get_event(); t.cat = cat;
+    Timed t; t.a = get_event(); t.b = get_event(); t.cat = cat; t.sub = sub; t.flops = flops;
     cudaEventRecord(t.a, st);
     timed.push_back(t);
   }
@@ -205,11 +205,20 @@ struct blim_engine {
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ------------------------------------------------------------------------------------------------ GEMM wrappers
+// profile sub-categories (blim_profile_read_detail): which contraction a GEMM launch is
+enum { kProfQkv = 0, kProfOProj = 1, kProfGateUp = 2, kProfDown = 3, kProfLse = 4, kProfOtherGemm = 5, kProfAttn = 6, kProfNorm = 7, kProfCats = 8 };
+template <class Epi> struct EpiProf { static int sub(const blim_engine*, int) { return kProfOtherGemm; } };
+template <int D> struct EpiProf<EpiQkvRope<D>> { static int sub(const blim_engine*, int) { return kProfQkv; } };
+template <> struct EpiProf<EpiSwiglu> { static int sub(const blim_engine*, int) { return kProfGateUp; } };
+template <> struct EpiProf<EpiLse> { static int sub(const blim_engine*, int) { return kProfLse; } };
+template <int G> struct EpiProf<EpiResidT<G>> { static int sub(const blim_engine* e, int K) { return K == e->I ? kProfDown : kProfOProj; } };
+template <> struct EpiProf<EpiResidNorm> { static int sub(const blim_engine* e, int K) { return K == e->I ? kProfDown : kProfOProj; } };
+
 template <class Epi>
 static int gemm(blim_engine* e, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const typename Epi::Params& p,
                 cudaStream_t st) {
   if (M <= 0) return 0;
-  e->tic(0, st);
+  e->tic(0, st, EpiProf<Epi>::sub(e, K), 2.0 * M * static_cast<double>(N) * K);
   cudaError_t r = launch_gemm<Epi>(e->gemm, A, lda, W, ldw, M, N, K, p, st);
   e->toc(st);
   if (r != cudaSuccess) return e->fail_cuda("tcgen05 gemm launch", r);
@@ -605,7 +614,9 @@ static int upload(blim_engine* e, DevBuf& dst, const void* src, size_t bytes, cu
 
 static int rmsnorm(blim_engine* e, bf16* out, const float* x0, const float* x1, const int* idx, const float* w, int R, cudaStream_t st) {
   if (R <= 0) return 0;
+  e->tic(2, st);
   rmsnorm_kernel<<<R, 256, 0, st>>>(out, x0, x1, idx, w, R, e->H, e->cfg.rms_norm_eps);
+  e->toc(st);
   CKL();
   return 0;
 }
@@ -1440,8 +1451,8 @@ extern "C" int blim_profile_read(blim_engine* e, double* gemm_ms, double* attn_m
   if (!e) return 1;
   CKE(cudaSetDevice(e->device));
   CKE(cudaDeviceSynchronize());
-  double ms[2] = {0.0, 0.0};
-  int64_t n[2] = {0, 0};
+  double ms[3] = {0.0, 0.0, 0.0};
+  int64_t n[3] = {0, 0, 0};
   for (auto& t : e->timed) {
     float f = 0.f;
     if (cudaEventElapsedTime(&f, t.a, t.b) == cudaSuccess) { ms[t.cat] += f; n[t.cat]++; }
@@ -1453,6 +1464,24 @@ extern "C" int blim_profile_read(blim_engine* e, double* gemm_ms, double* attn_m
   if (attn_ms) *attn_ms = ms[1];
   if (gemm_launches) *gemm_launches = n[0];
   if (attn_launches) *attn_launches = n[1];
+  return 0;
+}
+
+// Per-kind breakdown of the same event intervals WITHOUT resetting them (call before blim_profile_read): index
+// 0 QKV+RoPE, 1 o_proj, 2 gate|up+SwiGLU, 3 down_proj, 4 LM/TVG head + log-sum-exp, 5 other GEMMs (projectors, visual head),
+// 6 attention, 7 RMSNorm; ms = summed device time, flops = executed 2*M*N*K of the GEMM launches (0 for 6, 7).
+extern "C" int blim_profile_read_detail(blim_engine* e, int n, double* ms, double* flops, int64_t* launches) {
+  if (!e) return 1;
+  if (n < kProfCats || !ms || !flops || !launches) return e->fail("blim_profile_read_detail: need room for 8 categories");
+  CKE(cudaSetDevice(e->device));
+  CKE(cudaDeviceSynchronize());
+  for (int i = 0; i < n; ++i) { ms[i] = 0.0; flops[i] = 0.0; launches[i] = 0; }
+  for (auto& t : e->timed) {
+    float f = 0.f;
+    if (cudaEventElapsedTime(&f, t.a, t.b) != cudaSuccess) continue;
+    const int c = t.cat == 0 ? t.sub : (t.cat == 1 ? kProfAttn : kProfNorm);
+    ms[c] += f; flops[c] += t.flops; launches[c]++;
+  }
   return 0;
 }
 

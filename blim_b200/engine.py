@@ -322,6 +322,15 @@ class Engine:
         self._check(self.lib.blim_profile_read(self.h, ctypes.byref(g), ctypes.byref(a), ctypes.byref(ng), ctypes.byref(na)))
         return dict(gemm_ms=g.value, attn_ms=a.value, gemm_launches=ng.value, attn_launches=na.value)
 
+    PROFILE_KINDS = ("qkv_rope", "o_proj", "gate_up_swiglu", "down_proj", "head_lse", "other_gemm", "attention", "rmsnorm")
+
+    def profile_read_detail(self):
+        """-> {kind: dict(ms, flops, launches)} of the intervals recorded so far; does not reset (call before profile_read)."""
+        n = len(self.PROFILE_KINDS)
+        ms, fl, ln = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_int64 * n)()
+        self._check(self.lib.blim_profile_read_detail(self.h, n, ms, fl, ln))
+        return {k: dict(ms=ms[i], flops=fl[i], launches=ln[i]) for i, k in enumerate(self.PROFILE_KINDS)}
+
     def debug_umma(self, A, B, b_mn_major, lbo=0, sbo=0, kstep=0):
         """Single-CTA tcgen05 probe (see blim_debug_umma): A [128, K] bf16, B [N, K] or (b_mn_major) [K, N] bf16 -> fp32 [128, N]."""
         with torch.cuda.device(self.device):

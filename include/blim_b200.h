@@ -140,6 +140,11 @@ double blim_gemm_flops(const blim_engine* e);
  * count per kernel family since the last read, and resets. */
 int blim_profile(blim_engine* e, int enable);
 int blim_profile_read(blim_engine* e, double* gemm_ms, double* attn_ms, int64_t* gemm_launches, int64_t* attn_launches);
+/* Per-kind breakdown of the intervals recorded so far, without resetting them (call it before blim_profile_read).
+ * n >= 8 entries per array: 0 QKV+RoPE GEMM, 1 o_proj, 2 gate|up+SwiGLU, 3 down_proj, 4 LM / TVG head + log-sum-exp,
+ * 5 other GEMMs (projectors, visual head), 6 attention, 7 RMSNorm.  ms = summed device time, flops = executed 2*M*N*K
+ * of the GEMM launches (0 for attention / RMSNorm). */
+int blim_profile_read_detail(blim_engine* e, int n, double* ms, double* flops, int64_t* launches);
 
 /* Debug / unit-test entry: C = epilogue(A[M,K] · W[N,K]^T) with the engine's tcgen05 GEMM.
  * epilogue: 0 = bf16 store, 1 = bf16 store + bias, 2 = bf16 store + bias + GELU, 3 = fp32 store,
