@@ -210,12 +210,14 @@ def evaluation(model, data_loader, device, tokenizer, args):
     video, tvg_video_labels = [], []
     vtg_ids, vtg_labels, vtg_masks = [], [], []
     tvg_ids, tvg_labels, tvg_masks = [], [], []
-    for data in data_loader:                                           # retrieval_utils.py:182-193
-        video += [v for v in data["video"]]
-        vtg_ids += data["vtg_ids"]; vtg_labels += data["vtg_labels"]; vtg_masks += data["vtg_masks"]
-        tvg_ids += data["tvg_ids"]; tvg_labels += data["tvg_labels"]; tvg_masks += data["tvg_masks"]
-        tvg_video_labels.append(data["tvg_video_labels"])
-    tvg_video_labels = torch.cat(tvg_video_labels, dim=0)
+    staged = getattr(getattr(data_loader, "dataset", data_loader), "staged_corpus", None)   # blim_b200.dataset.stage_corpus
+    if staged is None:
+        for data in data_loader:                                       # retrieval_utils.py:182-193
+            video += [v for v in data["video"]]
+            vtg_ids += data["vtg_ids"]; vtg_labels += data["vtg_labels"]; vtg_masks += data["vtg_masks"]
+            tvg_ids += data["tvg_ids"]; tvg_labels += data["tvg_labels"]; tvg_masks += data["tvg_masks"]
+            tvg_video_labels.append(data["tvg_video_labels"])
+        tvg_video_labels = torch.cat(tvg_video_labels, dim=0)
     zero_shot = args.resume == "" and args.eval                         # retrieval_utils.py:199
     scores = getattr(args, "iv2_scores", None)
     if scores is None:
@@ -226,11 +228,13 @@ def evaluation(model, data_loader, device, tokenizer, args):
     full = not zero_shot
 
     # pad-stripped ragged texts go straight to the engine (padding_ids + the mask strip of mvf:333-334 cancel out)
-    m.ensure_videos(video)
-    eng.set_texts(TEXTS_VTG, vtg_ids, vtg_labels, vtg_masks)
-    eng.set_texts(TEXTS_TVG, tvg_ids, tvg_labels, tvg_masks)
-    if full:
-        m.ensure_vocab(data_loader.dataset.video_vocab, tvg_video_labels)
+    if staged is None:
+        m.ensure_videos(video)
+        eng.set_texts(TEXTS_VTG, vtg_ids, vtg_labels, vtg_masks)
+        eng.set_texts(TEXTS_TVG, tvg_ids, tvg_labels, tvg_masks)
+        if full:
+            m.ensure_vocab(data_loader.dataset.video_vocab, tvg_video_labels)
+    # else: features, token tables and the device-built video vocabulary are already in the engine
     m.set_tvg_prefix_length(data_loader.dataset.tvg_prefix_length)      # retrieval_utils.py:210
 
     plan = PairPlan(v2t_iv2.float(), t2v_iv2.float(), args.topk, eng.device, engine=eng)
