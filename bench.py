@@ -117,6 +117,23 @@ def measured_peaks():
     return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel (gate|up + SwiGLU tcgen05 GEMM) from the committed `ncu --set full`
+    capture (profiles/r01_traffic_*.json, written by tools/ncu_summary.py + the curation step in profiles/README.md);
+    None when no capture is committed.  Returns (bytes, detail dict)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic_*.json")))
+    if not files:
+        return None, None
+    rows = json.load(open(files[-1]))["launches"]
+    top = max((r for r in rows if r["kind"] == "gate_up_swiglu"), key=lambda r: r["ms"], default=None)
+    if top is None:
+        return None, None
+    return top["traffic_bytes"], {"file": os.path.relpath(files[-1], ROOT), "kernel": top["kernel"], "M": top["M"],
+                                  "algorithmic_bytes": top["algorithmic_bytes"], "traffic_over_algorithmic": top["traffic_over_algorithmic"],
+                                  "per_kind_traffic_over_algorithmic": {r["kind"]: r["traffic_over_algorithmic"] for r in rows}}
+
+
 def algorithmic_flops(cfg, corpus, plan, cpn=True, full=True):
     """FLOPs the algorithm needs -- non-padding tokens, every shared prefix once (including the chat-template
     header shared by all video prefixes / all TVG text prefixes), logits only at scored positions, and in the last layer
@@ -350,8 +367,10 @@ def main():
     share = 1.0 / world
     gemm_s = prof["gemm_ms"] / 1000.0 / args.steps
     achieved = f_gemm * share / gemm_s / 1e12 if gemm_s > 0 else None
+    traffic, traffic_detail = ncu_traffic()
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all epilogues)", "achieved": achieved, "peak": peaks["bf16_sustained"],
-                "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": traffic,
+                "traffic_detail": traffic_detail,
                 "peak_source": f"{peaks['source']} (sustained cuBLAS bf16; burst {peaks['bf16_burst']})",
                 "algorithmic_gemm_flops_per_step": f_gemm, "algorithmic_attention_flops_per_step": f_attn,
                 "executed_gemm_flops_per_step": executed_flops, "gemm_launches_per_step": prof["gemm_launches"] // max(1, args.steps),

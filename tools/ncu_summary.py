@@ -57,10 +57,13 @@ def shares(out, path):
         a = agg.setdefault(name, [0.0, 0])
         a[0] += v
         a[1] += 1
-    tot = sum(a[0] for a in agg.values())
+    # weight initialisation (torch RNG / casts) and the engine's one-off weight repacking run before the timed step
+    setup = lambda k: k.startswith(("native::", "at::")) or "repack_rows" in k or "elementwise" in k
+    tot = sum(a[0] for k, a in agg.items() if not setup(k))
     ks = [{"kernel": k, "share_pct": round(100 * a[0] / tot, 3), "ms": round(a[0], 3), "launches": a[1]} for k, a in
-          sorted(agg.items(), key=lambda kv: -kv[1][0])]
-    json.dump({"source": path, "total_ms": tot, "kernels": ks}, open(out, "w"), indent=1)
+          sorted(agg.items(), key=lambda kv: -kv[1][0]) if not setup(k)]
+    skipped = [{"kernel": k[:80], "ms": round(a[0], 3), "launches": a[1]} for k, a in agg.items() if setup(k)]
+    json.dump({"source": path, "total_ms": tot, "kernels": ks, "setup_kernels_excluded": skipped}, open(out, "w"), indent=1)
 
 
 if __name__ == "__main__":
