@@ -35,6 +35,31 @@ class FuseCfg(ctypes.Structure):
     ]
 
 
+class VisionCfg(ctypes.Structure):
+    """blim_vision_cfg (include/blim_vision.h)"""
+    _fields_ = [
+        ("image_size", c_i32), ("patch_size", c_i32), ("frames_per_clip", c_i32), ("hidden_size", c_i32), ("num_layers", c_i32),
+        ("num_heads", c_i32), ("mlp_hidden_size", c_i32), ("tome_tokens_per_frame", c_i32), ("max_clips", c_i32),
+        ("ln_eps", c_f32), ("final_ln_eps", c_f32),
+    ]
+
+
+# every symbol include/blim_vision.h declares
+VISION_SIGNATURES = {
+    "blim_vision_create": (c_int, [ctypes.POINTER(VisionCfg), c_int, ctypes.POINTER(c_void_p)]),
+    "blim_vision_destroy": (None, [c_void_p]),
+    "blim_vision_last_error": (c_char_p, [c_void_p]),
+    "blim_vision_load_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int, ctypes.POINTER(c_i64), c_int, c_void_p]),
+    "blim_vision_set_pos_embed": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "blim_vision_encode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "blim_vision_merge_tokens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "blim_vision_extract": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "blim_vision_kernel_launches": (c_i64, [c_void_p]),
+    "blim_vision_gemm_flops": (c_f64, [c_void_p]),
+    "blim_vision_profile": (c_int, [c_void_p, c_int]),
+    "blim_vision_profile_read": (c_int, [c_void_p, c_int, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64)]),
+}
+
 # name -> (restype, argtypes); every symbol include/blim_b200.h declares
 SIGNATURES = {
     "blim_create": (c_int, [ctypes.POINTER(ModelCfg), c_int, ctypes.POINTER(c_void_p)]),
@@ -82,7 +107,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing: build it with `python -m blim_b200.build` (no CPU fallback exists)")
     lib = ctypes.CDLL(LIB_PATH)
-    for name, (restype, argtypes) in SIGNATURES.items():
+    for name, (restype, argtypes) in list(SIGNATURES.items()) + list(VISION_SIGNATURES.items()):
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = restype
         fn.argtypes = argtypes

@@ -16,7 +16,8 @@ LIB = os.path.join(CSRC, "libblim_b200.so")
 STAMP = os.path.join(CSRC, ".build_stamp")
 
 SOURCES = ["engine.cu"]
-HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join(ROOT, "include", "blim_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join(ROOT, "include", "blim_b200.h"),
+                                                                              os.path.join(ROOT, "include", "blim_vision.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -47,10 +47,11 @@ struct AttnParamsTc {
   int a_row0;                 // row offset of this layer inside the tensor map of the prefix K / V buffers
   int b_row0;                 // row offset inside the tensor map of the own-run K / V buffers
   const uint8_t* key_valid;   // per own token, nullptr = all valid
-  const int* tok_seq_start;   // [T] first token of the sequence each token belongs to
+  const int* tok_seq_start;   // [T] first token of the sequence each token belongs to (nullptr: no own-run keys at all)
   const AttnWorkTc* works;
   int n_q, n_kv, group;
   float scale_log2;
+  int q_stride;               // elements between the Q rows of consecutive tokens (n_q, or 3 * n_q for a packed [Q|K|V] buffer)
 };
 
 constexpr int kTcKeys = 64;       // keys per chunk
@@ -108,10 +109,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_cons
   const int tok_local = tid / G, head = tid - tok_local * G;
   const bool row_ok = tok_local < w.n_tok;
   const int rt = w.tok0 + (row_ok ? tok_local : 0);        // run token index of the row
-  const int seq_lo = row_ok ? __ldg(p.tok_seq_start + rt) : 0;
+  const int seq_lo = (row_ok && p.tok_seq_start != nullptr) ? __ldg(p.tok_seq_start + rt) : 0;
   {
     // Q row -> swizzled K-major tile (zero-filled for padding rows)
-    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH;
+    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.q_stride + (kvh * G + head) * DH;
 #pragma unroll
     for (int c = 0; c < DH / 8; ++c)
       cp_async16(s_q + (c >> 3) * 16384 + sw128_offset(tid, (c & 7) * 8), src + c * 8, row_ok ? 16 : 0);
@@ -353,9 +354,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   const int tok_local = r / G, head = r - tok_local * G;
   const bool row_ok = tok_local < w.n_tok;
   const int rt = w.tok0 + (row_ok ? tok_local : 0);
-  const int seq_lo = row_ok ? __ldg(p.tok_seq_start + rt) : 0;
+  const int seq_lo = (row_ok && p.tok_seq_start != nullptr) ? __ldg(p.tok_seq_start + rt) : 0;
   {
-    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH;
+    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.q_stride + (kvh * G + head) * DH;
 #pragma unroll
     for (int cc = 0; cc < DH / 16; ++cc) {
       const int c = half * (DH / 16) + cc;
@@ -632,9 +633,9 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   const int tok_local = r / G, head = r - tok_local * G;
   const bool row_ok = tok_local < w.n_tok;
   const int rt = w.tok0 + (row_ok ? tok_local : 0);
-  const int seq_lo = row_ok ? __ldg(p.tok_seq_start + rt) : 0;
+  const int seq_lo = (row_ok && p.tok_seq_start != nullptr) ? __ldg(p.tok_seq_start + rt) : 0;
   {
-    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH;
+    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.q_stride + (kvh * G + head) * DH;
 #pragma unroll
     for (int cc = 0; cc < DH / 16; ++cc) {
       const int c = half * (DH / 16) + cc;

@@ -721,7 +721,7 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
       maps.vb = to_prefix_cache ? e->tm_vp : e->tm_vown;
       ap.key_valid = run.any_invalid ? e->d_key_valid.as<uint8_t>() : nullptr;
       ap.tok_seq_start = e->d_seq_start.as<int>(); ap.works = e->d_works.as<AttnWorkTc>();
-      ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G; ap.scale_log2 = scale_log2;
+      ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G; ap.scale_log2 = scale_log2; ap.q_stride = e->NQ;
       r = launch_attention_tc(maps, ap, n_works, e->NKV, e->DH, st, e->attn_tc_version);
     } else {
       AttnParams ap;
@@ -1529,3 +1529,7 @@ extern "C" int blim_debug_umma(blim_engine* e, const void* A, const void* B, flo
   e->launches++;
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ feature extractor
+// include/blim_vision.h: UMT ViT encoder + ToMe token merging on the same GEMM / attention kernels (one translation unit)
+#include "vision.cuh"

@@ -188,6 +188,45 @@ struct EpiResidT {
 
 using EpiResid = EpiResidT<2>;
 
+// resid[row, col] += acc + bias[col]   (ViT blocks: attn.proj / mlp.fc2 carry a bias, vision_tower_builder.py:96,53)
+struct EpiResidBias {
+  static constexpr int kGroups = 2;
+  struct Params {
+    float* resid;
+    int ldo;
+    const float* bias;
+  };
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
+    const bool row_ok = row < d.M;
+#pragma unroll 1
+    for (int c = half * (kBN / kGroups); c < (half + 1) * (kBN / kGroups); c += 32) {
+      float v[32];
+      tmem_ld32f(taddr + c, v);
+      const int col = n0 + c;
+      const int valid = d.N - col;
+      if (valid <= 0) continue;
+      if (row_ok) {
+        float* dst = p.resid + static_cast<size_t>(row) * p.ldo + col;
+        if (valid >= 32) {
+          float4* d4 = reinterpret_cast<float4*>(dst);
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 r = d4[i];
+            const float4 b = __ldg(b4 + i);
+            r.x += v[4 * i] + b.x; r.y += v[4 * i + 1] + b.y; r.z += v[4 * i + 2] + b.z; r.w += v[4 * i + 3] + b.w;
+            d4[i] = r;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < valid) dst[i] += v[i] + __ldg(p.bias + col + i);
+        }
+      }
+    }
+  }
+};
+
 // Residual add fused with the FIRST half of the following RMSNorm (reference: Qwen2DecoderLayer q2:784-789 + Qwen2RMSNorm
 // q2:93-98): x_new = resid + acc is written back in fp32, its bf16 copy `xb` becomes the A operand of the next GEMM
 // (un-normalised: the norm weight is folded into that GEMM's weight columns and 1/rms is applied per row in its

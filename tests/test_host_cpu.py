@@ -23,6 +23,12 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/blim_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    header = open(os.path.join(ROOT, "include", "blim_vision.h")).read()
+    declared = set(re.findall(r"\b(blim_vision_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 10
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/blim_vision.h but not exported"
+    assert declared == set(_lib.VISION_SIGNATURES), declared ^ set(_lib.VISION_SIGNATURES)
 
 
 def test_engine_fails_loudly_without_gpu():

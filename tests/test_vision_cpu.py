@@ -1,0 +1,79 @@
+"""Feature-extraction oracle (oracle/vision_oracle.py) and the host-side position table (blim_b200.vision) against
+tests/golden/vision_tiny.npz, which oracle/make_vision_golden.py wrote from the UNMODIFIED reference classes
+(UMTVisionTower / PretrainVisionTransformer / ToMe16_mlp_hd64) on CPU in fp32."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from blim_b200 import vision as V
+from oracle import vision_oracle as VO
+from oracle.make_vision_golden import CASES, make_frames, make_weights
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "vision_tiny.npz"))
+
+
+def _sub(name, key, arr):
+    if name == "tiny_224" and key == "pos_embed":
+        return arr[::8]
+    if name == "tiny_224" and key == "encoded":
+        return arr[:, ::8]
+    return arr
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_position_table_matches_reference(name):
+    cfg = CASES[name]["cfg"]
+    ref = GOLD[f"{name}/pos_embed"]
+    got = _sub(name, "pos_embed", V.position_table(cfg).numpy())
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 2e-6
+    got = _sub(name, "pos_embed", VO.position_table(cfg.image_size, cfg.patch_size, cfg.frames_per_clip, cfg.hidden_size, cfg.ckpt_num_frame).numpy())
+    assert np.abs(got - ref).max() <= 1e-6
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_encoder_and_merge_match_reference(name):
+    case = CASES[name]
+    cfg = case["cfg"]
+    w, frames = make_weights(case), make_frames(case)
+    with torch.no_grad():
+        enc = VO.vit_encode(w, cfg, frames)
+        assert np.abs(_sub(name, "encoded", enc.numpy()) - GOLD[f"{name}/encoded"]).max() <= 2e-5
+        target = cfg.tome_tokens_per_frame * cfg.frames_per_clip
+        merged, edge, node_idx = VO.merge_tokens(enc, target, cfg.num_heads, debug=True)
+    # index decisions of the first round: bit-exact (sorted positions [0, r) merge into dst, the rest stay)
+    np.testing.assert_array_equal(edge.numpy().astype(np.int32), GOLD[f"{name}/round1_edge"])
+    r = int(GOLD[f"{name}/round1_r"])
+    dst = np.take_along_axis(node_idx.numpy(), edge.numpy()[:, :r], axis=1)
+    np.testing.assert_array_equal(dst.astype(np.int32), GOLD[f"{name}/round1_dst"])
+    assert merged.shape == GOLD[f"{name}/merged"].shape
+    assert np.abs(merged.numpy() - GOLD[f"{name}/merged"]).max() <= 5e-5
+
+
+def test_merge_schedule_edge_cases():
+    """Odd token counts and a target reachable in one round (mm_projector_builder.py:110-117)."""
+    g = torch.Generator().manual_seed(0)
+    for p, target in ((145, 64), (100, 64), (65, 64), (513, 64)):
+        x = torch.randn(2, p, 128, generator=g)
+        out = VO.merge_tokens(x, target, heads=2)
+        assert out.shape == (2, target, 128)
+        # merging is a weighted average: the size-weighted token sum is conserved (target * mean == sum / sizes...) ->
+        # check the plain sum of x against the sum of (out * size) through a second pass with unit features
+        ones = VO.merge_tokens(torch.ones(2, p, 128), target, heads=2)
+        assert torch.allclose(ones, torch.ones_like(ones), atol=1e-6)
+
+
+def test_reference_vision_live():
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree not present (GPU box)")
+    from oracle.make_vision_golden import run_reference
+    live = run_reference(CASES["tiny_96"])
+    for k, v in live.items():
+        ref = GOLD[f"tiny_96/{k}"]
+        if np.issubdtype(np.asarray(v).dtype, np.integer):
+            np.testing.assert_array_equal(v, ref)
+        else:
+            assert np.abs(np.asarray(v) - ref).max() <= 1e-6, k
