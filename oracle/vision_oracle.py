@@ -93,11 +93,12 @@ def bipartite_matching(metric, r):
     edge_idx = node_max.argsort(dim=-1, descending=True, stable=True)[..., None]
     unm_idx, src_idx = edge_idx[..., r:, :], edge_idx[..., :r, :]
     dst_idx = node_idx[..., None].gather(dim=-2, index=src_idx)
-    return unm_idx, src_idx, dst_idx, node_idx, edge_idx[..., 0], r
+    return unm_idx, src_idx, dst_idx, node_idx, edge_idx[..., 0], r, node_max
 
 
 def merge_tokens(x, target, heads, debug=False):
-    """x [b, p, c] fp32 -> [b, target, c]; debug=True also returns the first round's (edge_idx, node_idx)."""
+    """x [b, p, c] fp32 -> [b, target, c]; debug=True also returns the first round's (edge_idx, node_idx, node_max).
+    Equal node_max values are ordered by index (stable sort); the reference leaves that order unspecified."""
     b, p, c = x.shape
     rs, tmp = [], p
     assert tmp > target
@@ -110,9 +111,9 @@ def merge_tokens(x, target, heads, debug=False):
     size, first = None, None
     for r in rs:
         metric = x.reshape(b, p, heads, c // heads).mean(2)
-        unm_idx, src_idx, dst_idx, node_idx, edge_idx, r = bipartite_matching(metric, r)
+        unm_idx, src_idx, dst_idx, node_idx, edge_idx, r, node_max = bipartite_matching(metric, r)
         if first is None:
-            first = (edge_idx.clone(), node_idx.clone())
+            first = (edge_idx.clone(), node_idx.clone(), node_max.clone())
 
         def merge(t):
             src, dst = t[..., ::2, :], t[..., 1::2, :]
@@ -128,7 +129,7 @@ def merge_tokens(x, target, heads, debug=False):
         size = merge(size)
         x = x / size
         p = x.shape[1]
-    return (x, first[0], first[1]) if debug else x
+    return ((x,) + first) if debug else x
 
 
 def extract(w, cfg, frames):

@@ -42,7 +42,7 @@ def test_oracle_encoder_and_merge_match_reference(name):
         enc = VO.vit_encode(w, cfg, frames)
         assert np.abs(_sub(name, "encoded", enc.numpy()) - GOLD[f"{name}/encoded"]).max() <= 2e-5
         target = cfg.tome_tokens_per_frame * cfg.frames_per_clip
-        merged, edge, node_idx = VO.merge_tokens(enc, target, cfg.num_heads, debug=True)
+        merged, edge, node_idx, _ = VO.merge_tokens(enc, target, cfg.num_heads, debug=True)
     # index decisions of the first round: bit-exact (sorted positions [0, r) merge into dst, the rest stay)
     np.testing.assert_array_equal(edge.numpy().astype(np.int32), GOLD[f"{name}/round1_edge"])
     r = int(GOLD[f"{name}/round1_r"])
