@@ -861,6 +861,321 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   if (warp == 0) tmem_dealloc<1>(tmem, kTcTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------ v4: dedicated issue warp
+// Same data flow as v3 (two S accumulators in TMEM, K and V double-buffered), but every TMA and tcgen05.mma is issued by a
+// NINTH warp that does nothing else.  In v2 / v3 thread 0 issues them between its own softmax work, so warp 0 executes
+// ~2x the instructions of the other warps and the whole CTA waits for it at every __syncthreads: the per-chunk critical
+// path was warp 0's instruction stream (ncu: 42 % issue utilisation, 17 % tensor pipe on the ViT shapes).  Here the
+// 256 softmax threads only talk to the issue warp through mbarriers:
+//     bar_s[2]      S(c) complete                      (tcgen05.commit)      -> softmax threads, issue warp
+//     bar_sfree[2]  every thread holds its S(c) row    (256 arrivals)        -> issue warp may overwrite that accumulator
+//     bar_p         P(c) in shared memory, O rescaled  (256 arrivals)        -> issue warp starts Oc = P V
+//     bar_o         Oc of chunk c complete             (tcgen05.commit)      -> P tile / V stage free, O readable
+// and among themselves through a 256-thread named barrier for the row-maximum exchange.  S(c+1) = Q K(c+1)^T is issued as
+// soon as S(c) completes, i.e. it runs under the softmax of chunk c.
+constexpr int kTc4Threads = 288;
+
+template <int DH>
+constexpr int attn_tc4_smem_bytes() {
+  // Q (DH/64 x 16 KB) + 2 x K + 2 x V (DH/64 x 8 KB each) + P (16 KB) + max exchange (512 B) + barriers (96 B)
+  return (DH / 64) * 16384 + 4 * (DH / 64) * 8192 + 16384 + 512 + 96;
+}
+
+__device__ __forceinline__ void softmax_group_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int DH>
+__global__ void __launch_bounds__(kTc4Threads, 2)
+attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_constant__ CUtensorMap tm_va,
+                     const __grid_constant__ CUtensorMap tm_kb, const __grid_constant__ CUtensorMap tm_vb, const AttnParamsTc p) {
+  constexpr int kSub = DH / 64;
+  constexpr uint32_t kChunkBytes = kSub * 8192;
+  constexpr float kGrow = 8.0f;
+  extern __shared__ __align__(1024) uint8_t smem_tc4[];
+  uint8_t* s_q = smem_tc4;
+  uint8_t* s_k = s_q + kSub * 16384;           // two stages
+  uint8_t* s_v = s_k + 2 * kSub * 8192;        // two stages
+  uint8_t* s_p = s_v + 2 * kSub * 8192;
+  __nv_bfloat16* s_mx = reinterpret_cast<__nv_bfloat16*>(s_p + 16384);   // [2][128] row maxima of the two half-row threads
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 16384 + 512);
+  uint64_t* bar_s = bars;        // [2]
+  uint64_t* bar_k = bars + 2;    // [2]
+  uint64_t* bar_v = bars + 4;    // [2]
+  uint64_t* bar_o = bars + 6;
+  uint64_t* bar_sfree = bars + 7;   // [2]
+  uint64_t* bar_p = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const AttnWorkTc w = p.works[blockIdx.x];
+  const int kvh = blockIdx.y;
+  const int G = p.group;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool issuer = warp == 8;                 // warp 8: TMA + MMA issue only
+  const int r = tid & 127, half = (tid >> 7) & 1;
+
+  if (tid == 0) {
+    if (smem_u32(smem_tc4) & 1023u) __trap();   // the swizzled tiles need a 1024-byte aligned base
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&bar_sfree[0], 256);
+    mbar_init(&bar_sfree[1], 256);
+    mbar_init(bar_p, 256);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_ka);
+    tma_prefetch_desc(&tm_va);
+    tma_prefetch_desc(&tm_kb);
+    tma_prefetch_desc(&tm_vb);
+  }
+  if (warp == 0) tmem_alloc<1>(tmem_slot, kTcTmemCols);
+
+  const int tok_local = r / G, head = r - tok_local * G;
+  const bool row_ok = tok_local < w.n_tok;
+  const int rt = w.tok0 + (row_ok ? tok_local : 0);
+  const int seq_lo = (row_ok && p.tok_seq_start != nullptr) ? __ldg(p.tok_seq_start + rt) : 0;
+  if (!issuer) {
+    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.q_stride + (kvh * G + head) * DH;
+#pragma unroll
+    for (int cc = 0; cc < DH / 16; ++cc) {
+      const int c = half * (DH / 16) + cc;
+      cp_async16(s_q + (c >> 3) * 16384 + sw128_offset(r, (c & 7) * 8), src + c * 8, row_ok ? 16 : 0);
+    }
+    cp_async_commit();
+  }
+
+  const int n_a = (w.a_len + kTcKeys - 1) / kTcKeys;
+  const int own_len = w.tok0 + w.n_tok - w.kb0;
+  const int n_chunks = n_a + (own_len + kTcKeys - 1) / kTcKeys;
+
+  auto chunk_keys = [&](int c, int& nk, int& key0, bool& own, int& tm_row) {
+    if (c < n_a) {
+      own = false;
+      key0 = c * kTcKeys;
+      nk = min(kTcKeys, w.a_len - key0);
+      tm_row = p.a_row0 + w.a_start + key0;
+    } else {
+      own = true;
+      key0 = w.kb0 + (c - n_a) * kTcKeys;
+      nk = min(kTcKeys, w.tok0 + w.n_tok - key0);
+      tm_row = p.b_row0 + key0 + w.b_off;
+    }
+  };
+  auto stage = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tm_row) {
+    mbar_arrive_expect_tx(bar, kChunkBytes);
+#pragma unroll
+    for (int sub = 0; sub < kSub; ++sub) tma_load_2d(dst + sub * 8192, tm, bar, kvh * DH + sub * 64, tm_row);
+  };
+  auto stage_k = [&](int c) {
+    int nk, key0, row; bool own;
+    chunk_keys(c, nk, key0, own, row);
+    stage(s_k + (c & 1) * kSub * 8192, own ? &tm_kb : &tm_ka, &bar_k[c & 1], row);
+  };
+  auto stage_v = [&](int c) {
+    int nk, key0, row; bool own;
+    chunk_keys(c, nk, key0, own, row);
+    stage(s_v + (c & 1) * kSub * 8192, own ? &tm_vb : &tm_va, &bar_v[c & 1], row);
+  };
+  auto issue_s = [&](int c, uint32_t tmem) {   // S[c & 1] = Q K(c)^T (tid 0 only)
+    int nk, key0, row; bool own;
+    chunk_keys(c, nk, key0, own, row);
+    const int nk16 = (nk + 15) & ~15;
+    mbar_wait(&bar_k[c & 1], static_cast<uint32_t>((c >> 1) & 1));
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16_ex(128, nk16, 0);
+    const uint32_t k_base = smem_u32(s_k) + (c & 1) * kSub * 8192;
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+      const uint64_t da = make_smem_desc_sw128(smem_u32(s_q) + (kk >> 2) * 16384 + (kk & 3) * 32);
+      const uint64_t db = make_smem_desc_sw128(k_base + (kk >> 2) * 8192 + (kk & 3) * 32);
+      umma_bf16<1>(tmem + (c & 1) * 64, da, db, idesc, kk != 0 ? 1u : 0u);
+    }
+    umma_commit(&bar_s[c & 1]);
+  };
+
+  cp_async_wait<0>();
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();   // barriers initialised, TMEM allocated, Q staged
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (issuer) {
+    // ===================================================== issue warp (one elected lane)
+    if ((tid & 31) == 0) {
+      stage_k(0);
+      stage_v(0);
+      if (n_chunks > 1) { stage_k(1); stage_v(1); }
+      issue_s(0, tmem);
+      for (int c = 0; c < n_chunks; ++c) {
+        int nk, key0, tm_row_unused; bool own;
+        chunk_keys(c, nk, key0, own, tm_row_unused);
+        const int nk16 = (nk + 15) & ~15;
+        mbar_wait(&bar_s[c & 1], static_cast<uint32_t>((c >> 1) & 1));   // S(c) complete: its K stage is free
+        if (c + 1 < n_chunks) {
+          if (c >= 1) mbar_wait(&bar_sfree[(c + 1) & 1], static_cast<uint32_t>(((c - 1) >> 1) & 1));   // S(c-1) rows are in registers
+          issue_s(c + 1, tmem);
+        }
+        if (c + 2 < n_chunks) stage_k(c + 2);
+        if (c >= 1) {
+          mbar_wait(bar_o, static_cast<uint32_t>((c - 1) & 1));          // Oc(c-1) complete: its V stage is free
+          if (c + 1 < n_chunks) stage_v(c + 1);
+        }
+        mbar_wait(bar_p, static_cast<uint32_t>(c & 1));                  // P(c) written, O rescaled
+        mbar_wait(&bar_v[c & 1], static_cast<uint32_t>((c >> 1) & 1));
+        tc_fence_after();
+        const uint32_t idesc = make_idesc_bf16_ex(128, DH, 1);
+        const uint32_t v_base = smem_u32(s_v) + (c & 1) * kSub * 8192;
+        for (int kk = 0; kk < nk16 / 16; ++kk) {
+          const uint64_t da = make_smem_desc_sw128(smem_u32(s_p) + kk * 32);
+          const uint64_t db = make_smem_desc_raw(v_base + kk * 2048, 8192, 1024);
+          umma_bf16<1>(tmem + 128, da, db, idesc, (c > 0 || kk != 0) ? 1u : 0u);
+        }
+        umma_commit(bar_o);
+      }
+      mbar_wait(bar_o, static_cast<uint32_t>((n_chunks - 1) & 1));       // keep the CTA's shared memory alive until the last MMA read it
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();   // matches the softmax threads' final barrier (TMEM release)
+    return;
+  }
+  // ===================================================== 256 softmax threads
+  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  const uint32_t t_o = t_row + 128 + half * (DH / 2);      // this thread's DH/2 O columns (S0: [0,64), S1: [64,128))
+
+  float m_ref = -INFINITY, l_part = 0.f;
+
+  for (int c = 0; c < n_chunks; ++c) {
+    int nk, key0, tm_row_unused; bool own;
+    chunk_keys(c, nk, key0, own, tm_row_unused);
+    const int nk16 = (nk + 15) & ~15;
+
+    mbar_wait(&bar_s[c & 1], static_cast<uint32_t>((c >> 1) & 1));
+    __syncwarp();
+    tc_fence_after();
+    float sv[32];
+    if (half * 32 < nk16) {   // warp-uniform
+      uint32_t raw[32];
+      tmem_ld32(t_row + (c & 1) * 64 + half * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(raw[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sv[i] = 0.f;
+    }
+    float cmax = -INFINITY;
+    if (!own && nk == kTcKeys) {   // CTA-uniform fast path: a full chunk of the shared prefix, every key visible
+#pragma unroll
+      for (int i = 0; i < 32; ++i) cmax = fmaxf(cmax, sv[i]);
+    } else {
+      int j_lo = 0, j_hi = nk - 1;
+      if (own) {
+        j_lo = max(0, seq_lo - key0);
+        j_hi = min(nk - 1, rt - key0);
+      }
+      // visible keys among this thread's 32 as a bit mask: [j_lo, j_hi] clipped to the half's window
+      const int lo = max(j_lo - half * 32, 0), hi = min(j_hi - half * 32, 31);
+      uint32_t vmask = (hi >= lo) ? ((0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo)) : 0u;
+      if (own && p.key_valid != nullptr && vmask != 0u) {
+        const uint8_t* kv = p.key_valid + key0 + half * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (((vmask >> i) & 1u) && kv[i] == 0) vmask &= ~(1u << i);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float val = ((vmask >> i) & 1u) ? sv[i] : -INFINITY;
+        sv[i] = val;
+        cmax = fmaxf(cmax, val);
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(&bar_sfree[c & 1]);                  // this thread's S(c) values are in registers
+    s_mx[half * 128 + r] = __float2bfloat16(cmax);   // both threads of the row use the same (bf16-rounded) pair of maxima
+    softmax_group_sync();   // [A] maxima visible
+    const float cmax_s = fmaxf(__bfloat162float(s_mx[r]), __bfloat162float(s_mx[128 + r])) * p.scale_log2;
+    softmax_group_sync();   // [A'] maxima read: the exchange buffer may be overwritten by the next chunk
+
+    if (c > 0) {
+      mbar_wait(bar_o, static_cast<uint32_t>((c - 1) & 1));   // Oc(c-1) complete: P tile free, O readable
+      __syncwarp();
+      tc_fence_after();
+    }
+    float corr = 1.f;
+    bool grow = false;
+    if (c == 0) {
+      m_ref = cmax_s;
+    } else if (cmax_s > m_ref + kGrow) {
+      grow = true;
+      corr = exp2f(m_ref - cmax_s);
+      m_ref = cmax_s;
+      l_part *= corr;
+    }
+    if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll
+      for (int h = 0; h < DH / 64; ++h) {
+        uint32_t raw[32];
+        tmem_ld32(t_o + h * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
+        tmem_st32(t_o + h * 32, raw);
+      }
+      tmem_st_wait();
+    }
+    const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+    float csum = 0.f;
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p0 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
+        const float p1 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
+        csum += p0 + p1;
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+        pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      if (half * 32 + j8 * 8 < nk16) *reinterpret_cast<uint4*>(s_p + sw128_offset(r, half * 32 + j8 * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    l_part += csum;
+
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(bar_p);     // [B] this thread's part of P(c) is written, its O columns are rescaled
+  }
+
+  // ---- O / l -> bf16   (the P tile is free: reuse it to add the two half-row sums)
+  mbar_wait(bar_o, static_cast<uint32_t>((n_chunks - 1) & 1));
+  __syncwarp();
+  tc_fence_after();
+  float* s_l = reinterpret_cast<float*>(s_p);
+  s_l[half * 128 + r] = l_part;
+  softmax_group_sync();
+  const float l = s_l[r] + s_l[128 + r];
+  const float inv = l > 0.f ? 1.0f / l : 0.f;
+  __nv_bfloat16* dst = p.o + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH + half * (DH / 2);
+#pragma unroll
+  for (int h = 0; h < DH / 64; ++h) {
+    uint32_t raw[32];
+    tmem_ld32(t_o + h * 32, raw);
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(raw[c8 * 8 + 2 * e]) * inv, __uint_as_float(raw[c8 * 8 + 2 * e + 1]) * inv);
+          pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        *reinterpret_cast<uint4*>(dst + h * 32 + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc<1>(tmem, kTcTmemCols);
+}
+
 // Host: blocks of 128 / G consecutive tokens over every prefix-sharing group of consecutive sequences, plus the
 // per-token "first token of my sequence" table.
 inline void build_attn_works_tc(const AttnSeq* seqs, int n_seqs, int group, std::vector<AttnWorkTc>& works, std::vector<int>& tok_seq_start,
@@ -948,10 +1263,45 @@ inline cudaError_t launch_attention_tc3_impl(const AttnTcMaps& m, const AttnPara
   return cudaGetLastError();
 }
 
+// v4 needs two 112.7 KB CTAs of 288 threads per SM; returns cudaErrorLaunchOutOfResources (caller falls back) otherwise.
+template <int DH>
+inline cudaError_t launch_attention_tc4_impl(const AttnTcMaps& m, const AttnParamsTc& p, dim3 grid, cudaStream_t stream) {
+  static int state = 0;
+  if (state == 0) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc4_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc4_smem_bytes<DH>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc4_kernel<DH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncAttributes fa;
+    int blocks = 0, dev = 0, smem_sm = 0, regs_sm = 0;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, attention_tc4_kernel<DH>);
+    if (e == cudaSuccess) e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+    if (e == cudaSuccess) {
+      const int smem_cta = ((attn_tc4_smem_bytes<DH>() + static_cast<int>(fa.sharedSizeBytes) + 127) & ~127) + 1024;
+      const int regs_cta = kTc4Threads * ((fa.numRegs + 7) & ~7);
+      blocks = std::min(smem_sm / smem_cta, regs_sm / regs_cta);
+    } else {
+      cudaGetLastError();
+    }
+    state = (e == cudaSuccess && blocks >= 2) ? 1 : -1;
+    if (getenv("BLIM_DEBUG")) fprintf(stderr, "[blim] attention v4 (head_dim %d): %d CTA(s) per SM with %d B dynamic smem -> %s\n", DH, blocks,
+                                      attn_tc4_smem_bytes<DH>(), state > 0 ? "used" : "falling back");
+  }
+  if (state < 0) return cudaErrorLaunchOutOfResources;
+  attention_tc4_kernel<DH><<<grid, kTc4Threads, attn_tc4_smem_bytes<DH>(), stream>>>(m.ka, m.va, m.kb, m.vb, p);
+  return cudaGetLastError();
+}
+
 inline cudaError_t launch_attention_tc(const AttnTcMaps& m, const AttnParamsTc& p, int n_works, int n_kv_heads, int head_dim,
                                        cudaStream_t stream, int version = 2) {
   if (n_works <= 0) return cudaSuccess;
   dim3 grid(static_cast<unsigned>(n_works), static_cast<unsigned>(n_kv_heads));
+  if (version == 4) {
+    cudaError_t e = head_dim == 128 ? launch_attention_tc4_impl<128>(m, p, grid, stream)
+                  : head_dim == 64 ? launch_attention_tc4_impl<64>(m, p, grid, stream) : cudaErrorInvalidValue;
+    if (e != cudaErrorLaunchOutOfResources) return e;
+    version = 2;
+  }
   if (version == 3) {
     cudaError_t e = head_dim == 128 ? launch_attention_tc3_impl<128>(m, p, grid, stream)
                   : head_dim == 64 ? launch_attention_tc3_impl<64>(m, p, grid, stream) : cudaErrorInvalidValue;

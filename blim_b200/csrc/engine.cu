@@ -289,7 +289,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
   {
     const char* a = getenv("BLIM_ATTN");
     e->attn_tc = !(a && std::string(a) == "mma");
-    e->attn_tc_version = (a && std::string(a) == "tc1") ? 1 : (a && std::string(a) == "tc3") ? 3 : 2;
+    e->attn_tc_version = (a && std::string(a) == "tc1") ? 1 : (a && std::string(a) == "tc3") ? 3 : (a && std::string(a) == "tc4") ? 4 : 2;
     const char* rs = getenv("BLIM_ROOT");
     e->root_share = !(rs && std::string(rs) == "0");
     const char* f = getenv("BLIM_FUSE_NORM");

@@ -66,7 +66,52 @@ __device__ __forceinline__ float block_sum_256(float v, float* sh) {
   return t;
 }
 
-// nn.LayerNorm over the last dimension (biased variance, fp32 statistics); one 256-thread CTA per row, C <= 4096.
+// nn.LayerNorm over the last dimension (biased variance, fp32 statistics): one WARP per row, the row lives in registers as
+// NV float4 per lane (C = 128 * NV), 8 rows per 256-thread CTA, no shared memory and no block barrier.
+template <typename OutT, int NV>
+__global__ void __launch_bounds__(256) layernorm_warp_kernel(OutT* __restrict__ out, const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ b, int rows, float eps) {
+  constexpr int C = 128 * NV;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * C);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = src[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(w4 + lane + 32 * i), h = __ldg(b4 + lane + 32 * i);
+    const float y0 = v[i].x * rstd * g.x + h.x, y1 = v[i].y * rstd * g.y + h.y, y2 = v[i].z * rstd * g.z + h.z, y3 = v[i].w * rstd * g.w + h.w;
+    if constexpr (sizeof(OutT) == 2) {
+      uint2 u;
+      u.x = pack_bf16x2(y0, y1);
+      u.y = pack_bf16x2(y2, y3);
+      reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * C)[lane + 32 * i] = u;
+    } else {
+      reinterpret_cast<float4*>(out + static_cast<size_t>(row) * C)[lane + 32 * i] = make_float4(y0, y1, y2, y3);
+    }
+  }
+}
+
+// generic fallback (any C <= 4096): one 256-thread CTA per row
 template <typename OutT>
 __global__ void __launch_bounds__(256) layernorm_kernel(OutT* __restrict__ out, const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, int C, float eps) {
@@ -98,6 +143,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(OutT* __restrict__ out, 
       if constexpr (sizeof(OutT) == 2) dst[c] = __float2bfloat16(y); else dst[c] = y;
     }
   }
+}
+
+template <typename OutT>
+static void launch_layernorm(OutT* out, const float* x, const float* w, const float* b, int rows, int C, float eps, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  if (C == 1024) layernorm_warp_kernel<OutT, 8><<<grid, 256, 0, st>>>(out, x, w, b, rows, eps);
+  else if (C == 128) layernorm_warp_kernel<OutT, 1><<<grid, 256, 0, st>>>(out, x, w, b, rows, eps);
+  else if (C == 768) layernorm_warp_kernel<OutT, 6><<<grid, 256, 0, st>>>(out, x, w, b, rows, eps);
+  else layernorm_kernel<OutT><<<rows, 256, 0, st>>>(out, x, w, b, C, eps);
 }
 
 // ---- ToMe (mm_projector_builder.py:6-130), one grid.y slice per clip
@@ -281,6 +335,7 @@ struct blim_vision {
   int device = 0;
   int S, P, Wp, L, FPC, C, NL, NH, DH, F, KP, TL;   // TL = tokens per clip = FPC * L
   int max_clips = 16;
+  int attn_version = 2;   // BLIM_VIS_ATTN=2|3|4: attention_tc2 / tc3 / tc4 kernel
   std::string err;
   GemmLaunchCtx gemm;
   DevBuf w_patch, b_patch, lnf_w, lnf_b, pos;
@@ -373,6 +428,7 @@ extern "C" int blim_vision_create(const blim_vision_cfg* cfg, int device, blim_v
   if (v->TL <= cfg->tome_tokens_per_frame * v->FPC) { delete v; return bad("a clip must have more tokens than the merging target (mm_projector_builder.py:110)"); }
   v->gemm.num_sms = prop.multiProcessorCount;
   v->gemm.cta_group = 2;
+  if (const char* a = getenv("BLIM_VIS_ATTN")) v->attn_version = (atoi(a) >= 2 && atoi(a) <= 4) ? atoi(a) : 2;
   v->blocks.resize(v->NL);
   const size_t M = static_cast<size_t>(v->max_clips) * v->TL;
   const size_t na = (v->TL + 1) / 2;
@@ -555,7 +611,7 @@ static int vis_encode(blim_vision* v, const void* frames, int dtype, int n_frame
   for (int l = 0; l < v->NL; ++l) {
     const VisBlockW& w = v->blocks[l];
     v->tic(2, st);
-    layernorm_kernel<bf16><<<M, 256, 0, st>>>(xn, x, w.ln1_w.as<float>(), w.ln1_b.as<float>(), C, v->cfg.ln_eps);
+    launch_layernorm<bf16>(xn, x, w.ln1_w.as<float>(), w.ln1_b.as<float>(), M, C, v->cfg.ln_eps, st);
     v->toc(st);
     VCL();
     {
@@ -563,7 +619,7 @@ static int vis_encode(blim_vision* v, const void* frames, int dtype, int n_frame
       if (vis_gemm<EpiStore<bf16, true, false>>(v, xn, C, w.w_qkv.as<bf16>(), C, M, 3 * C, C, p, st)) return 1;
     }
     v->tic(1, st);
-    cudaError_t r = launch_attention_tc(maps, ap, v->n_works, v->NH, v->DH, st, 2);
+    cudaError_t r = launch_attention_tc(maps, ap, v->n_works, v->NH, v->DH, st, v->attn_version);
     v->toc(st);
     if (r != cudaSuccess) return v->fail_cuda("attention launch", r);
     v->launches++;
@@ -572,7 +628,7 @@ static int vis_encode(blim_vision* v, const void* frames, int dtype, int n_frame
       if (vis_gemm<EpiResidBias>(v, v->attn.as<bf16>(), C, w.w_proj.as<bf16>(), C, M, C, C, p, st)) return 1;
     }
     v->tic(2, st);
-    layernorm_kernel<bf16><<<M, 256, 0, st>>>(xn, x, w.ln2_w.as<float>(), w.ln2_b.as<float>(), C, v->cfg.ln_eps);
+    launch_layernorm<bf16>(xn, x, w.ln2_w.as<float>(), w.ln2_b.as<float>(), M, C, v->cfg.ln_eps, st);
     v->toc(st);
     VCL();
     {
@@ -585,7 +641,7 @@ static int vis_encode(blim_vision* v, const void* frames, int dtype, int n_frame
     }
   }
   v->tic(2, st);
-  layernorm_kernel<float><<<M, 256, 0, st>>>(feat_out, x, v->lnf_w.as<float>(), v->lnf_b.as<float>(), C, v->cfg.final_ln_eps);
+  launch_layernorm<float>(feat_out, x, v->lnf_w.as<float>(), v->lnf_b.as<float>(), M, C, v->cfg.final_ln_eps, st);
   v->toc(st);
   VCL();
   return 0;
