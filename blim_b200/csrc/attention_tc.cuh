@@ -870,15 +870,16 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
 //     bar_s[2]      S(c) complete                      (tcgen05.commit)      -> softmax threads, issue warp
 //     bar_sfree[2]  every thread holds its S(c) row    (256 arrivals)        -> issue warp may overwrite that accumulator
 //     bar_p         P(c) in shared memory, O rescaled  (256 arrivals)        -> issue warp starts Oc = P V
-//     bar_o         Oc of chunk c complete             (tcgen05.commit)      -> P tile / V stage free, O readable
+//     bar_o[2]      Oc of chunk c complete             (tcgen05.commit)      -> P tile / V stage free, O readable
 // and among themselves through a 256-thread named barrier for the row-maximum exchange.  S(c+1) = Q K(c+1)^T is issued as
-// soon as S(c) completes, i.e. it runs under the softmax of chunk c.
+// soon as S(c) completes, i.e. it runs under the softmax of chunk c.  head_dim 64 has room for TWO P tiles: P(c+1) is
+// written while Oc(c) = P(c) V(c) is still running, and a thread waits for Oc(c-1) only when it must rescale O.
 constexpr int kTc4Threads = 288;
 
 template <int DH>
 constexpr int attn_tc4_smem_bytes() {
-  // Q (DH/64 x 16 KB) + 2 x K + 2 x V (DH/64 x 8 KB each) + P (16 KB) + max exchange (512 B) + barriers (96 B)
-  return (DH / 64) * 16384 + 4 * (DH / 64) * 8192 + 16384 + 512 + 96;
+  // Q (DH/64 x 16 KB) + 2 x K + 2 x V (DH/64 x 8 KB each) + P (16 KB; two for head_dim 64) + max exchange (512 B) + barriers (96 B)
+  return (DH / 64) * 16384 + 4 * (DH / 64) * 8192 + (DH == 64 ? 2 : 1) * 16384 + 512 + 96;
 }
 
 __device__ __forceinline__ void softmax_group_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -890,20 +891,22 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   constexpr int kSub = DH / 64;
   constexpr uint32_t kChunkBytes = kSub * 8192;
   constexpr float kGrow = 8.0f;
+  constexpr bool kPDouble = DH == 64;
+  constexpr int kPBytes = (kPDouble ? 2 : 1) * 16384;
   extern __shared__ __align__(1024) uint8_t smem_tc4[];
   uint8_t* s_q = smem_tc4;
   uint8_t* s_k = s_q + kSub * 16384;           // two stages
   uint8_t* s_v = s_k + 2 * kSub * 8192;        // two stages
   uint8_t* s_p = s_v + 2 * kSub * 8192;
-  __nv_bfloat16* s_mx = reinterpret_cast<__nv_bfloat16*>(s_p + 16384);   // [2][128] row maxima of the two half-row threads
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 16384 + 512);
+  __nv_bfloat16* s_mx = reinterpret_cast<__nv_bfloat16*>(s_p + kPBytes);   // [2][128] row maxima of the two half-row threads
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + kPBytes + 512);
   uint64_t* bar_s = bars;        // [2]
   uint64_t* bar_k = bars + 2;    // [2]
   uint64_t* bar_v = bars + 4;    // [2]
-  uint64_t* bar_o = bars + 6;
-  uint64_t* bar_sfree = bars + 7;   // [2]
-  uint64_t* bar_p = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* bar_o = bars + 6;    // [2]  Oc(c) -> bar_o[c & 1]
+  uint64_t* bar_sfree = bars + 8;   // [2]
+  uint64_t* bar_p = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const AttnWorkTc w = p.works[blockIdx.x];
   const int kvh = blockIdx.y;
@@ -914,7 +917,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
 
   if (tid == 0) {
     if (smem_u32(smem_tc4) & 1023u) __trap();   // the swizzled tiles need a 1024-byte aligned base
-    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
     mbar_init(&bar_sfree[0], 256);
     mbar_init(&bar_sfree[1], 256);
     mbar_init(bar_p, 256);
@@ -957,10 +960,15 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
       tm_row = p.b_row0 + key0 + w.b_off;
     }
   };
+  // The issue warp runs its loop with all 32 lanes (uniform control flow: waits, addresses and descriptors live in uniform
+  // registers) and only the instruction that talks to the TMA / tensor core is predicated on the elected lane.
+  const bool lead = issuer && elect_one() != 0;
   auto stage = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tm_row) {
-    mbar_arrive_expect_tx(bar, kChunkBytes);
+    if (lead) {
+      mbar_arrive_expect_tx(bar, kChunkBytes);
 #pragma unroll
-    for (int sub = 0; sub < kSub; ++sub) tma_load_2d(dst + sub * 8192, tm, bar, kvh * DH + sub * 64, tm_row);
+      for (int sub = 0; sub < kSub; ++sub) tma_load_2d(dst + sub * 8192, tm, bar, kvh * DH + sub * 64, tm_row);
+    }
   };
   auto stage_k = [&](int c) {
     int nk, key0, row; bool own;
@@ -972,7 +980,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
     chunk_keys(c, nk, key0, own, row);
     stage(s_v + (c & 1) * kSub * 8192, own ? &tm_vb : &tm_va, &bar_v[c & 1], row);
   };
-  auto issue_s = [&](int c, uint32_t tmem) {   // S[c & 1] = Q K(c)^T (tid 0 only)
+  auto issue_s = [&](int c, uint32_t tmem) {   // S[c & 1] = Q K(c)^T (issue warp)
     int nk, key0, row; bool own;
     chunk_keys(c, nk, key0, own, row);
     const int nk16 = (nk + 15) & ~15;
@@ -980,13 +988,16 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
     tc_fence_after();
     const uint32_t idesc = make_idesc_bf16_ex(128, nk16, 0);
     const uint32_t k_base = smem_u32(s_k) + (c & 1) * kSub * 8192;
+    if (lead) {
 #pragma unroll
-    for (int kk = 0; kk < DH / 16; ++kk) {
-      const uint64_t da = make_smem_desc_sw128(smem_u32(s_q) + (kk >> 2) * 16384 + (kk & 3) * 32);
-      const uint64_t db = make_smem_desc_sw128(k_base + (kk >> 2) * 8192 + (kk & 3) * 32);
-      umma_bf16<1>(tmem + (c & 1) * 64, da, db, idesc, kk != 0 ? 1u : 0u);
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        const uint64_t da = make_smem_desc_sw128(smem_u32(s_q) + (kk >> 2) * 16384 + (kk & 3) * 32);
+        const uint64_t db = make_smem_desc_sw128(k_base + (kk >> 2) * 8192 + (kk & 3) * 32);
+        umma_bf16<1>(tmem + (c & 1) * 64, da, db, idesc, kk != 0 ? 1u : 0u);
+      }
+      umma_commit(&bar_s[c & 1]);
     }
-    umma_commit(&bar_s[c & 1]);
+    __syncwarp();
   };
 
   cp_async_wait<0>();
@@ -996,8 +1007,8 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (issuer) {
-    // ===================================================== issue warp (one elected lane)
-    if ((tid & 31) == 0) {
+    // ===================================================== issue warp
+    {
       stage_k(0);
       stage_v(0);
       if (n_chunks > 1) { stage_k(1); stage_v(1); }
@@ -1012,23 +1023,37 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
           issue_s(c + 1, tmem);
         }
         if (c + 2 < n_chunks) stage_k(c + 2);
-        if (c >= 1) {
-          mbar_wait(bar_o, static_cast<uint32_t>((c - 1) & 1));          // Oc(c-1) complete: its V stage is free
-          if (c + 1 < n_chunks) stage_v(c + 1);
+        if (c >= 1 && c + 1 < n_chunks) {
+          mbar_wait(&bar_o[(c - 1) & 1], static_cast<uint32_t>(((c - 1) >> 1) & 1));   // Oc(c-1) complete: its V stage is free
+          stage_v(c + 1);
         }
         mbar_wait(bar_p, static_cast<uint32_t>(c & 1));                  // P(c) written, O rescaled
         mbar_wait(&bar_v[c & 1], static_cast<uint32_t>((c >> 1) & 1));
         tc_fence_after();
         const uint32_t idesc = make_idesc_bf16_ex(128, DH, 1);
         const uint32_t v_base = smem_u32(s_v) + (c & 1) * kSub * 8192;
-        for (int kk = 0; kk < nk16 / 16; ++kk) {
-          const uint64_t da = make_smem_desc_sw128(smem_u32(s_p) + kk * 32);
-          const uint64_t db = make_smem_desc_raw(v_base + kk * 2048, 8192, 1024);
-          umma_bf16<1>(tmem + 128, da, db, idesc, (c > 0 || kk != 0) ? 1u : 0u);
+        if (lead) {
+          if (nk16 == kTcKeys) {
+#pragma unroll
+            for (int kk = 0; kk < kTcKeys / 16; ++kk) {
+              const uint64_t da = make_smem_desc_sw128(smem_u32(s_p) + (kPDouble ? (c & 1) * 16384 : 0) + kk * 32);
+              const uint64_t db = make_smem_desc_raw(v_base + kk * 2048, 8192, 1024);
+              umma_bf16<1>(tmem + 128, da, db, idesc, (c > 0 || kk != 0) ? 1u : 0u);
+            }
+          } else {
+            for (int kk = 0; kk < nk16 / 16; ++kk) {
+              const uint64_t da = make_smem_desc_sw128(smem_u32(s_p) + (kPDouble ? (c & 1) * 16384 : 0) + kk * 32);
+              const uint64_t db = make_smem_desc_raw(v_base + kk * 2048, 8192, 1024);
+              umma_bf16<1>(tmem + 128, da, db, idesc, (c > 0 || kk != 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&bar_o[c & 1]);
         }
-        umma_commit(bar_o);
+        __syncwarp();
       }
-      mbar_wait(bar_o, static_cast<uint32_t>((n_chunks - 1) & 1));       // keep the CTA's shared memory alive until the last MMA read it
+      // keep the CTA's shared memory alive until the last MMAs read it
+      if (n_chunks > 1) mbar_wait(&bar_o[(n_chunks - 2) & 1], static_cast<uint32_t>(((n_chunks - 2) >> 1) & 1));
+      mbar_wait(&bar_o[(n_chunks - 1) & 1], static_cast<uint32_t>(((n_chunks - 1) >> 1) & 1));
     }
     __syncwarp();
     tc_fence_before();
@@ -1093,10 +1118,15 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
     const float cmax_s = fmaxf(__bfloat162float(s_mx[r]), __bfloat162float(s_mx[128 + r])) * p.scale_log2;
     softmax_group_sync();   // [A'] maxima read: the exchange buffer may be overwritten by the next chunk
 
-    if (c > 0) {
-      mbar_wait(bar_o, static_cast<uint32_t>((c - 1) & 1));   // Oc(c-1) complete: P tile free, O readable
+    if constexpr (!kPDouble) {
+      if (c > 0) {
+        mbar_wait(&bar_o[(c - 1) & 1], static_cast<uint32_t>(((c - 1) >> 1) & 1));   // Oc(c-1) complete: P tile free, O readable
+        __syncwarp();
+        tc_fence_after();
+      }
+    } else if (c >= 2) {
+      mbar_wait(&bar_o[c & 1], static_cast<uint32_t>(((c - 2) >> 1) & 1));           // Oc(c-2) complete: P tile (c & 1) is free
       __syncwarp();
-      tc_fence_after();
     }
     float corr = 1.f;
     bool grow = false;
@@ -1109,6 +1139,11 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
       l_part *= corr;
     }
     if (__any_sync(0xffffffffu, grow)) {
+      if constexpr (kPDouble) {   // O is only touched here: wait for the accumulation that is still in flight
+        mbar_wait(&bar_o[(c - 1) & 1], static_cast<uint32_t>(((c - 1) >> 1) & 1));
+        __syncwarp();
+        tc_fence_after();
+      }
 #pragma unroll
       for (int h = 0; h < DH / 64; ++h) {
         uint32_t raw[32];
@@ -1133,7 +1168,8 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
         __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
         pk[e] = *reinterpret_cast<uint32_t*>(&b2);
       }
-      if (half * 32 + j8 * 8 < nk16) *reinterpret_cast<uint4*>(s_p + sw128_offset(r, half * 32 + j8 * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      if (half * 32 + j8 * 8 < nk16)
+        *reinterpret_cast<uint4*>(s_p + (kPDouble ? (c & 1) * 16384 : 0) + sw128_offset(r, half * 32 + j8 * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
     l_part += csum;
 
@@ -1143,7 +1179,8 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   }
 
   // ---- O / l -> bf16   (the P tile is free: reuse it to add the two half-row sums)
-  mbar_wait(bar_o, static_cast<uint32_t>((n_chunks - 1) & 1));
+  if (n_chunks > 1) mbar_wait(&bar_o[(n_chunks - 2) & 1], static_cast<uint32_t>(((n_chunks - 2) >> 1) & 1));
+  mbar_wait(&bar_o[(n_chunks - 1) & 1], static_cast<uint32_t>(((n_chunks - 1) >> 1) & 1));
   __syncwarp();
   tc_fence_after();
   float* s_l = reinterpret_cast<float*>(s_p);

@@ -229,10 +229,13 @@ __global__ void __launch_bounds__(256) tome_match_kernel(float* __restrict__ nod
   }
 }
 
-// edge_idx = argsort(node_max, descending) with ties in index order (mm_projector_builder.py:30), and the merge target of
-// every sorted position dst_of[q] = node_idx[edge_idx[q]] (:34).  One CTA per clip, bitonic network over n_sort >= na keys.
-__global__ void __launch_bounds__(1024) tome_sort_kernel(int* __restrict__ edge, int* __restrict__ dst_of, const float* __restrict__ node_max,
-                                                         const int* __restrict__ node_idx, int na, int n_sort) {
+// edge_idx = argsort(node_max, descending) with ties in index order (mm_projector_builder.py:30), then the r merged sources
+// (sorted positions [0, r)) grouped by their merge target dst = node_idx[edge_idx[q]] (:34): csr_src lists the positions q
+// ordered by (dst, q), csr_start / csr_end delimit every odd token's group -- scatter_add visits the sources of a
+// destination in ascending q, and so does the merge kernel.  One CTA per clip, bitonic networks over n_sort >= na keys.
+__global__ void __launch_bounds__(1024) tome_sort_kernel(int* __restrict__ edge, int* __restrict__ csr_src, int* __restrict__ csr_start,
+                                                         int* __restrict__ csr_end, const float* __restrict__ node_max,
+                                                         const int* __restrict__ node_idx, int na, int nb, int r, int n_sort) {
   extern __shared__ uint8_t sort_smem[];
   float* key = reinterpret_cast<float*>(sort_smem);
   int* idx = reinterpret_cast<int*>(sort_smem + static_cast<size_t>(n_sort) * 4);
@@ -258,9 +261,33 @@ __global__ void __launch_bounds__(1024) tome_sort_kernel(int* __restrict__ edge,
     }
   }
   const int* ni = node_idx + static_cast<size_t>(blockIdx.x) * na;
-  for (int i = threadIdx.x; i < na; i += blockDim.x) {
-    edge[static_cast<size_t>(blockIdx.x) * na + i] = idx[i];
-    dst_of[static_cast<size_t>(blockIdx.x) * na + i] = ni[idx[i]];
+  int* key2 = reinterpret_cast<int*>(key);   // (dst << 14 | q) of the merged sources, INT_MAX padding
+  for (int i = threadIdx.x; i < n_sort; i += blockDim.x) {
+    if (i < na) edge[static_cast<size_t>(blockIdx.x) * na + i] = idx[i];
+    key2[i] = i < r ? ((ni[idx[i]] << 14) | i) : 0x7fffffff;
+  }
+  for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+    csr_start[static_cast<size_t>(blockIdx.x) * nb + j] = 0;
+    csr_end[static_cast<size_t>(blockIdx.x) * nb + j] = 0;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n_sort; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < n_sort / 2; t += blockDim.x) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int hi = lo | j;
+        const bool up = (lo & k) == 0;
+        const int ka = key2[lo], kb = key2[hi];
+        if ((ka < kb) != up) { key2[lo] = kb; key2[hi] = ka; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < r; i += blockDim.x) {
+    const int kv = key2[i], j = kv >> 14;
+    csr_src[static_cast<size_t>(blockIdx.x) * na + i] = kv & 16383;
+    if (i == 0 || (key2[i - 1] >> 14) != j) csr_start[static_cast<size_t>(blockIdx.x) * nb + j] = i;
+    if (i == r - 1 || (key2[i + 1] >> 14) != j) csr_end[static_cast<size_t>(blockIdx.x) * nb + j] = i + 1;
   }
 }
 
@@ -269,9 +296,9 @@ __global__ void __launch_bounds__(1024) tome_sort_kernel(int* __restrict__ edge,
 // sorted order, :40-43), divided by the merged size.  size_in == nullptr: all ones (first round).
 __global__ void __launch_bounds__(256) tome_merge_kernel(float* __restrict__ x_out, float* __restrict__ size_out, const float* __restrict__ x_in,
                                                          const float* __restrict__ size_in, const int* __restrict__ edge,
-                                                         const int* __restrict__ dst_of, int p, int r, int C) {
-  extern __shared__ int s_dst[];   // dst_of[0, r)
-  const int na = (p + 1) / 2;
+                                                         const int* __restrict__ csr_src, const int* __restrict__ csr_start,
+                                                         const int* __restrict__ csr_end, int p, int r, int C) {
+  const int na = (p + 1) / 2, nb = p / 2;
   const int clip = blockIdx.y, k = blockIdx.x;
   const float* xin = x_in + static_cast<size_t>(clip) * p * C;
   const float* sin_ = size_in ? size_in + static_cast<size_t>(clip) * p : nullptr;
@@ -285,9 +312,8 @@ __global__ void __launch_bounds__(256) tome_merge_kernel(float* __restrict__ x_o
     return;
   }
   const int j = k - (na - r);
-  const int* dof = dst_of + static_cast<size_t>(clip) * na;
-  for (int q = threadIdx.x; q < r; q += 256) s_dst[q] = dof[q];
-  __syncthreads();
+  const int q0 = csr_start[static_cast<size_t>(clip) * nb + j], q1 = csr_end[static_cast<size_t>(clip) * nb + j];
+  const int* src = csr_src + static_cast<size_t>(clip) * na;
   const int tok = 2 * j + 1;
   const float s0 = sin_ ? sin_[tok] : 1.f;
   float acc[16];
@@ -297,9 +323,8 @@ __global__ void __launch_bounds__(256) tome_merge_kernel(float* __restrict__ x_o
     acc[i] = c < C ? xin[static_cast<size_t>(tok) * C + c] * s0 : 0.f;
   }
   float ssum = s0;
-  for (int q = 0; q < r; ++q) {
-    if (s_dst[q] != j) continue;   // CTA-uniform
-    const int st = 2 * eg[q];
+  for (int t = q0; t < q1; ++t) {   // ascending sorted position: the order scatter_add accumulates in
+    const int st = 2 * eg[src[t]];
     const float ss = sin_ ? sin_[st] : 1.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -343,7 +368,7 @@ struct blim_vision {
   std::vector<VisBlockW> blocks;
   // workspaces
   DevBuf patches, x, xn, qkv, attn, act, feat, works;
-  DevBuf t_x[2], t_size[2], t_metric, t_nmax, t_nidx, t_edge, t_dst;
+  DevBuf t_x[2], t_size[2], t_metric, t_nmax, t_nidx, t_edge, t_dst, t_cstart, t_cend;
   int works_clips = 0;
   int n_works = 0;
   int64_t launches = 0;
@@ -389,7 +414,7 @@ extern "C" void blim_vision_destroy(blim_vision* v) {
   if (!v) return;
   cudaSetDevice(v->device);
   DevBuf* bufs[] = {&v->w_patch, &v->b_patch, &v->lnf_w, &v->lnf_b, &v->pos, &v->patches, &v->x, &v->xn, &v->qkv, &v->attn, &v->act, &v->feat,
-                    &v->works, &v->t_x[0], &v->t_x[1], &v->t_size[0], &v->t_size[1], &v->t_metric, &v->t_nmax, &v->t_nidx, &v->t_edge, &v->t_dst};
+                    &v->works, &v->t_x[0], &v->t_x[1], &v->t_size[0], &v->t_size[1], &v->t_metric, &v->t_nmax, &v->t_nidx, &v->t_edge, &v->t_dst, &v->t_cstart, &v->t_cend};
   for (DevBuf* b : bufs) b->release();
   for (auto& bw : v->blocks) {
     DevBuf* wb[] = {&bw.ln1_w, &bw.ln1_b, &bw.ln2_w, &bw.ln2_b, &bw.w_qkv, &bw.b_qkv, &bw.w_proj, &bw.b_proj, &bw.w_fc1, &bw.b_fc1, &bw.w_fc2, &bw.b_fc2};
@@ -428,7 +453,8 @@ extern "C" int blim_vision_create(const blim_vision_cfg* cfg, int device, blim_v
   if (v->TL <= cfg->tome_tokens_per_frame * v->FPC) { delete v; return bad("a clip must have more tokens than the merging target (mm_projector_builder.py:110)"); }
   v->gemm.num_sms = prop.multiProcessorCount;
   v->gemm.cta_group = 2;
-  if (const char* a = getenv("BLIM_VIS_ATTN")) v->attn_version = (atoi(a) >= 2 && atoi(a) <= 4) ? atoi(a) : 2;
+  v->attn_version = dh == 64 ? 4 : 2;   // v4 (issue warp, two P tiles) wins at head_dim 64; at 128 its 96-register budget spills
+  if (const char* a = getenv("BLIM_VIS_ATTN")) v->attn_version = (atoi(a) >= 2 && atoi(a) <= 4) ? atoi(a) : v->attn_version;
   v->blocks.resize(v->NL);
   const size_t M = static_cast<size_t>(v->max_clips) * v->TL;
   const size_t na = (v->TL + 1) / 2;
@@ -437,7 +463,8 @@ extern "C" int blim_vision_create(const blim_vision_cfg* cfg, int device, blim_v
       {&v->act, M * v->F * 2}, {&v->feat, M * v->C * 4}, {&v->pos, static_cast<size_t>(v->TL) * v->C * 4},
       {&v->t_x[0], M * v->C * 4}, {&v->t_x[1], M * v->C * 4}, {&v->t_size[0], M * 4}, {&v->t_size[1], M * 4},
       {&v->t_metric, M * (v->C / v->NH) * 4}, {&v->t_nmax, v->max_clips * na * 4}, {&v->t_nidx, v->max_clips * na * 4},
-      {&v->t_edge, v->max_clips * na * 4}, {&v->t_dst, v->max_clips * na * 4}};
+      {&v->t_edge, v->max_clips * na * 4}, {&v->t_dst, v->max_clips * na * 4}, {&v->t_cstart, v->max_clips * na * 4},
+      {&v->t_cend, v->max_clips * na * 4}};
   for (auto& w : ws) {
     if (w.b->reserve(w.bytes) != cudaSuccess) {
       g_vision_create_error = "out of device memory for the extractor workspaces";
@@ -694,8 +721,9 @@ static int vis_merge(blim_vision* v, const float* x_in, int b, int p, int target
       VCK(cudaFuncSetAttribute(tome_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
       sort_attr = true;
     }
-    tome_sort_kernel<<<b, 1024, static_cast<size_t>(n_sort) * 8, st>>>(v->t_edge.as<int>(), v->t_dst.as<int>(), v->t_nmax.as<float>(), v->t_nidx.as<int>(),
-                                                                       na, n_sort);
+    tome_sort_kernel<<<b, 1024, static_cast<size_t>(n_sort) * 8, st>>>(v->t_edge.as<int>(), v->t_dst.as<int>(), v->t_cstart.as<int>(),
+                                                                       v->t_cend.as<int>(), v->t_nmax.as<float>(), v->t_nidx.as<int>(), na, pc / 2, r,
+                                                                       n_sort);
     VCL();
     if (round == 0) {
       if (edge_out) VCK(cudaMemcpyAsync(edge_out, v->t_edge.p, static_cast<size_t>(b) * na * 4, cudaMemcpyDeviceToDevice, st));
@@ -704,8 +732,8 @@ static int vis_merge(blim_vision* v, const float* x_in, int b, int p, int target
     const bool last = round + 1 == rs.size();
     float* dst = last ? out : v->t_x[round & 1].as<float>();
     float* dst_size = v->t_size[round & 1].as<float>();
-    tome_merge_kernel<<<dim3(pc - r, b), 256, static_cast<size_t>(std::max(r, 1)) * 4, st>>>(dst, dst_size, cur, cur_size, v->t_edge.as<int>(),
-                                                                                             v->t_dst.as<int>(), pc, r, C);
+    tome_merge_kernel<<<dim3(pc - r, b), 256, 0, st>>>(dst, dst_size, cur, cur_size, v->t_edge.as<int>(), v->t_dst.as<int>(),
+                                                       v->t_cstart.as<int>(), v->t_cend.as<int>(), pc, r, C);
     VCL();
     cur = dst;
     cur_size = dst_size;
