@@ -143,6 +143,7 @@ struct blim_engine {
 
   // workspaces
   DevBuf x, xn, q, attn, k_own, v_own, act, kp, vp, prefix_last, vis, proj_tmp, lm_a, pred, partial, tgt_logit, logp, uniq_scores;
+  DevBuf vis_in, d_vis_idx;  // projector input staging for non-contiguous video sets (gathered feature rows + their indices)
   DevBuf d_tok_slot, d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
   bool attn_tc = true;  // tcgen05 attention (BLIM_ATTN=mma selects the mma.sync kernel, tc1 the first tcgen05 kernel)
   int attn_tc_version = 2;
@@ -245,7 +246,7 @@ extern "C" void blim_destroy(blim_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   DevBuf* bufs[] = {&e->embed, &e->lm_head, &e->visual_head, &e->norm, &e->rope_cos, &e->rope_sin, &e->feats, &e->vocab, &e->tvg_vis,
-                    &e->x, &e->xn, &e->q, &e->attn, &e->k_own, &e->v_own, &e->act, &e->kp, &e->vp, &e->prefix_last, &e->vis,
+                    &e->x, &e->xn, &e->q, &e->attn, &e->k_own, &e->v_own, &e->act, &e->kp, &e->vp, &e->prefix_last, &e->vis, &e->vis_in, &e->d_vis_idx,
                     &e->proj_tmp, &e->lm_a, &e->pred, &e->partial, &e->tgt_logit, &e->logp, &e->uniq_scores, &e->d_tok_src,
                     &e->d_tok_pos, &e->d_key_valid, &e->d_seqs, &e->d_works, &e->d_idx, &e->d_targets, &e->d_row_off, &e->d_map, &e->d_seq_start, &e->ssq, &e->rstd, &e->d_tok_slot};
   for (DevBuf* b : bufs) b->release();
@@ -314,7 +315,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
       {&e->x, T * e->H * 4}, {&e->xn, T * e->H * 2}, {&e->q, T * e->NQ * 2}, {&e->attn, T * e->NQ * 2},
       {&e->k_own, T * e->NKVD * 2}, {&e->v_own, T * e->NKVD * 2}, {&e->act, T * static_cast<size_t>(e->I) * 2},
       {&e->kp, static_cast<size_t>(e->NL) * P * e->NKVD * 2}, {&e->vp, static_cast<size_t>(e->NL) * P * e->NKVD * 2},
-      {&e->prefix_last, static_cast<size_t>(e->Umax) * e->H * 4}, {&e->vis, P * e->H * 2}, {&e->proj_tmp, T * e->H * 2},
+      {&e->prefix_last, static_cast<size_t>(e->Umax) * e->H * 4}, {&e->vis, P * e->H * 2}, {&e->vis_in, P * e->MM * 2}, {&e->d_vis_idx, P * 4}, {&e->proj_tmp, T * e->H * 2},
       {&e->lm_a, T * e->H * 2}, {&e->pred, T * e->MM * 2}, {&e->tgt_logit, T * 4}, {&e->logp, T * 4},
       {&e->d_tok_src, T * 4}, {&e->d_tok_pos, T * 4}, {&e->d_key_valid, T}, {&e->d_seqs, T * sizeof(AttnSeq)},
       {&e->d_works, (T * e->G / kAttnRows + T + 1) * sizeof(AttnWorkTc)}, {&e->d_idx, T * 4}, {&e->d_targets, T * 4},
@@ -922,16 +923,23 @@ static int score_vtg(blim_engine* e, bool prior, const std::vector<std::pair<int
         const int v = unit_key[bu.unit].first;
         if (!vis_row0.count(v)) { vis_row0[v] = rows; rows += n_vis; }
       }
-      // videos are contiguous in e->feats only per video: project video by video groups of consecutive ids
-      for (auto it = vis_row0.begin(); it != vis_row0.end();) {
-        // merge consecutive video ids that also got consecutive row ranges
-        auto jt = it;
-        int cnt = 1;
-        auto nx = std::next(jt);
-        while (nx != vis_row0.end() && nx->first == jt->first + 1 && nx->second == jt->second + n_vis) { jt = nx; nx = std::next(jt); ++cnt; }
-        CKR(project(e, e->feats.as<bf16>() + static_cast<size_t>(it->first) * n_vis * e->MM, cnt * n_vis, 0,
-                    e->vis.as<bf16>() + static_cast<size_t>(it->second) * e->H, st));
-        it = nx;
+      // one projector pass per batch: a run of consecutive video ids is projected in place, anything else (e.g. the
+      // strided ids a rank owns in a multi-GPU run) is first gathered into a contiguous staging buffer
+      std::vector<std::pair<int, int>> by_row;   // (first row in e->vis, video)
+      for (const auto& kv : vis_row0) by_row.emplace_back(kv.second, kv.first);
+      std::sort(by_row.begin(), by_row.end());
+      bool contiguous = true;
+      for (size_t i = 1; i < by_row.size(); ++i) contiguous = contiguous && by_row[i].second == by_row[i - 1].second + 1;
+      if (contiguous) {
+        CKR(project(e, e->feats.as<bf16>() + static_cast<size_t>(by_row[0].second) * n_vis * e->MM, rows, 0, e->vis.as<bf16>(), st));
+      } else {
+        std::vector<int> idx(rows);
+        for (const auto& rv : by_row)
+          for (int i = 0; i < n_vis; ++i) idx[rv.first + i] = rv.second * n_vis + i;
+        CKR(upload(e, e->d_vis_idx, idx.data(), static_cast<size_t>(rows) * 4, st));
+        gather_rows_bf16_kernel<<<rows, 128, 0, st>>>(e->vis_in.as<bf16>(), e->feats.as<bf16>(), e->d_vis_idx.as<int>(), rows, e->MM);
+        CKL();
+        CKR(project(e, e->vis_in.as<bf16>(), rows, 0, e->vis.as<bf16>(), st));
       }
     }
     // ---- prefix run.  With a shared root (all units of the batch use the same prompt group) the header tokens are

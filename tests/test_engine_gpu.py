@@ -69,6 +69,22 @@ def test_small_workspace_batches_agree(golden_case):
         small.close()
 
 
+def test_strided_video_subsets_match_full_run(golden_case):
+    """What a rank of a multi-GPU run scores: the pairs of every W-th video (non-consecutive ids -> the projector input is
+    gathered).  Sharding must not change any score (retrieval.score_all shards by `owner % world`)."""
+    name, spec, cfg, weights, corpus, eng, gold = golden_case
+    ref = gold["v2t_vtg_lik"]
+    rows, cols = np.nonzero(ref != -100.0)
+    for kind in (VTG, TVG_PRIOR):
+        full = eng.score_pairs(kind, rows, cols).cpu().numpy()
+        for world in (2, 3):
+            got = np.empty_like(full)
+            for r in range(world):
+                mine = np.nonzero(rows % world == r)[0]
+                got[mine] = eng.score_pairs(kind, rows[mine], cols[mine]).cpu().numpy()
+            assert np.abs(got - full).max() < 2e-3, (kind, world, np.abs(got - full).max())
+
+
 def _mid_cfg():
     return ModelConfig(hidden_size=512, num_layers=3, num_heads=4, num_kv_heads=2, intermediate_size=1536, vocab_size=8192,
                        mm_hidden_size=1024, max_positions=2048, image_token_id=8000)
