@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libblim_b200.so")
+LIB_PATH = os.environ.get("BLIM_LIB") or os.path.join(_HERE, "csrc", "libblim_b200.so")   # BLIM_LIB: A/B runs against another build
 
 c_int = ctypes.c_int
 c_i32 = ctypes.c_int32

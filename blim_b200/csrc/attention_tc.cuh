@@ -336,6 +336,10 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   const int G = p.group;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r = tid & 127, half = tid >> 7;
+  // Warp 0 issues every TMA / tcgen05.mma with uniform control flow (all 32 lanes walk the issue code, so addresses and
+  // descriptors are computed once in uniform registers) and only the issuing instruction is predicated on the elected lane:
+  // the issue work sits on the CTA's critical path (everyone waits for warp 0 at the barriers).
+  const bool lead = warp == 0 ? elect_one() != 0 : false;
 
   if (tid == 0) {
     mbar_init(&bar_s, 1);
@@ -382,10 +386,12 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
       tm_row = p.b_row0 + key0 + w.b_off;
     }
   };
-  auto stage = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tm_row) {
-    mbar_arrive_expect_tx(bar, kChunkBytes);
+  auto stage = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tm_row) {   // warp 0
+    if (lead) {
+      mbar_arrive_expect_tx(bar, kChunkBytes);
 #pragma unroll
-    for (int sub = 0; sub < kSub; ++sub) tma_load_2d(dst + sub * 8192, tm, bar, kvh * DH + sub * 64, tm_row);
+      for (int sub = 0; sub < kSub; ++sub) tma_load_2d(dst + sub * 8192, tm, bar, kvh * DH + sub * 64, tm_row);
+    }
   };
   auto stage_k = [&](int c) {
     int nk, key0, row; bool own;
@@ -397,20 +403,23 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
     chunk_keys(c, nk, key0, own, row);
     stage(s_v + (c & 1) * kSub * 8192, own ? &tm_vb : &tm_va, &bar_v[c & 1], row);
   };
-  auto issue_s = [&](int c, uint32_t tmem) {   // S = Q K^T of chunk c (tid 0 only)
+  auto issue_s = [&](int c, uint32_t tmem) {   // S = Q K^T of chunk c (warp 0)
     int nk, key0, row; bool own;
     chunk_keys(c, nk, key0, own, row);
     const int nk16 = (nk + 15) & ~15;
     mbar_wait(&bar_k, static_cast<uint32_t>(c & 1));
     tc_fence_after();
     const uint32_t idesc = make_idesc_bf16_ex(128, nk16, 0);
+    if (lead) {
 #pragma unroll
-    for (int kk = 0; kk < DH / 16; ++kk) {
-      const uint64_t da = make_smem_desc_sw128(smem_u32(s_q) + (kk >> 2) * 16384 + (kk & 3) * 32);
-      const uint64_t db = make_smem_desc_sw128(smem_u32(s_k) + (kk >> 2) * 8192 + (kk & 3) * 32);
-      umma_bf16<1>(tmem, da, db, idesc, kk != 0 ? 1u : 0u);
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        const uint64_t da = make_smem_desc_sw128(smem_u32(s_q) + (kk >> 2) * 16384 + (kk & 3) * 32);
+        const uint64_t db = make_smem_desc_sw128(smem_u32(s_k) + (kk >> 2) * 8192 + (kk & 3) * 32);
+        umma_bf16<1>(tmem, da, db, idesc, kk != 0 ? 1u : 0u);
+      }
+      umma_commit(&bar_s);
     }
-    umma_commit(&bar_s);
+    __syncwarp();
   };
 
   cp_async_wait<0>();
@@ -419,7 +428,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   __syncthreads();   // barriers initialised, TMEM allocated, Q staged
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (tid == 0) {
+  if (warp == 0) {
     stage_k(0);
     stage_v(0);
     if (n_chunks > 1) stage_v(1);
@@ -480,14 +489,14 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
     s_x[half][r] = cmax;
     tc_fence_before();
     __syncthreads();   // [A] every S(c) value is in registers: the S columns and the K buffer are free
-    if (tid == 0 && c + 1 < n_chunks) stage_k(c + 1);
+    if (warp == 0 && c + 1 < n_chunks) stage_k(c + 1);
     const float cmax_s = fmaxf(s_x[0][r], s_x[1][r]) * p.scale_log2;   // -inf * positive = -inf
 
     // ---- Oc = P V of the previous chunk has to be complete before P / O are touched
     if (c > 0) {
       mbar_wait(&bar_o, static_cast<uint32_t>((c - 1) & 1));
       tc_fence_after();
-      if (tid == 0 && c + 1 < n_chunks) stage_v(c + 1);   // its buffer was read by chunk c-1
+      if (warp == 0 && c + 1 < n_chunks) stage_v(c + 1);   // its buffer was read by chunk c-1
       __syncwarp();
     }
     // ---- lazy rescale of O (TMEM) and of the running sum
@@ -534,17 +543,21 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();   // [B] P written, O rescaled
-    if (tid == 0) {
+    if (warp == 0) {
       mbar_wait(&bar_v[c & 1], static_cast<uint32_t>((c >> 1) & 1));
+      __syncwarp();
       tc_fence_after();
       const uint32_t idesc = make_idesc_bf16_ex(128, DH, 1);
       const uint32_t v_base = smem_u32(s_v) + (c & 1) * kSub * 8192;
-      for (int kk = 0; kk < nk16 / 16; ++kk) {
-        const uint64_t da = make_smem_desc_sw128(smem_u32(s_p) + kk * 32);
-        const uint64_t db = make_smem_desc_raw(v_base + kk * 2048, 8192, 1024);
-        umma_bf16<1>(tmem + 64, da, db, idesc, (c > 0 || kk != 0) ? 1u : 0u);
+      if (lead) {
+        for (int kk = 0; kk < nk16 / 16; ++kk) {
+          const uint64_t da = make_smem_desc_sw128(smem_u32(s_p) + kk * 32);
+          const uint64_t db = make_smem_desc_raw(v_base + kk * 2048, 8192, 1024);
+          umma_bf16<1>(tmem + 64, da, db, idesc, (c > 0 || kk != 0) ? 1u : 0u);
+        }
+        umma_commit(&bar_o);
       }
-      umma_commit(&bar_o);
+      __syncwarp();
       if (c + 1 < n_chunks) issue_s(c + 1, tmem);
     }
   }
