@@ -40,7 +40,8 @@ struct GemmCfg {
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+  static constexpr int kOutStageBytes = 8 * 32 * 80;  // per epilogue warp: 32 rows x (64 B + 16 B pad) for coalesced bf16 stores
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kOutStageBytes + 1024;
 };
 
 struct GemmDims {
@@ -110,7 +111,8 @@ __device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&v)[32]) {
 // at K = 1024 (the ViT's fc1) the epilogue of a 256-column tile otherwise takes longer than its mainloop.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // one MUFU.RCP (1 ulp), not the IEEE-rounded software path
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
@@ -134,7 +136,7 @@ struct EpiStore {
     int ldo;
     const float* bias;
   };
-  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half, uint8_t* wstage) {
     const bool row_ok = row < d.M;
 #pragma unroll 1
     for (int c = half * (kBN / 2); c < (half + 1) * (kBN / 2); c += 32) {
@@ -152,12 +154,31 @@ struct EpiStore {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
       }
-      if (row_ok) {
-        OutT* dst = p.out + static_cast<size_t>(row) * p.ldo + col;
-        if constexpr (sizeof(OutT) == 2)
-          store_row32_bf16(reinterpret_cast<__nv_bfloat16*>(dst), v, valid);
-        else
-          store_row32_f32(reinterpret_cast<float*>(dst), v, valid);
+      if constexpr (sizeof(OutT) == 2) {
+        if (valid >= 32) {   // warp-uniform
+          // Row-per-thread stores scatter every warp instruction over 32 rows (32 half-used sectors).  Stage the warp's
+          // 32 x 64 B through shared memory instead and store 8 rows x 64 contiguous bytes per instruction.
+          const int lane = threadIdx.x & 31;
+          uint4* srow = reinterpret_cast<uint4*>(wstage + lane * 80);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            srow[i] = make_uint4(pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                 pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+          __syncwarp();
+          const int r0 = row - lane;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rr = (lane >> 2) + 8 * j;
+            const uint4 val = *reinterpret_cast<const uint4*>(wstage + rr * 80 + (lane & 3) * 16);
+            if (r0 + rr < d.M)
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(r0 + rr) * p.ldo + col + (lane & 3) * 8) = val;
+          }
+          __syncwarp();
+        } else if (row_ok) {
+          store_row32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col, v, valid);
+        }
+      } else if (row_ok) {
+        store_row32_f32(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col, v, valid);
       }
     }
   }
@@ -171,7 +192,7 @@ struct EpiResidT {
     float* resid;
     int ldo;
   };
-  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half, uint8_t* wstage) {
     const bool row_ok = row < d.M;
 #pragma unroll 1
     for (int c = half * (kBN / kGroups); c < (half + 1) * (kBN / kGroups); c += 32) {
@@ -210,7 +231,7 @@ struct EpiResidBias {
     int ldo;
     const float* bias;
   };
-  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half, uint8_t* wstage) {
     const bool row_ok = row < d.M;
 #pragma unroll 1
     for (int c = half * (kBN / kGroups); c < (half + 1) * (kBN / kGroups); c += 32) {
@@ -254,7 +275,7 @@ struct EpiResidNorm {
     float* ssq;            // [M, 2 * n_tiles] out
     int ldo;
   };
-  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half, uint8_t* wstage) {
     const bool row_ok = row < d.M;
     float ss = 0.f;
 #pragma unroll 1
@@ -311,7 +332,7 @@ struct EpiQkvRope {
     int n_q, n_kv, max_pos;
     const float* rstd;     // [M] 1/rms of the (un-normalised) A rows, nullptr = A is already normalised
   };
-  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half, uint8_t* wstage) {
     constexpr int kHalf = kHeadDim / 2;
     static_assert(kHeadDim == 64 || kHeadDim == 128, "head_dim must be 64 or 128");
     const bool row_ok = row < d.M;
@@ -375,7 +396,7 @@ struct EpiSwiglu {
     int ldo;             // = I
     const float* rstd;   // [M] 1/rms of the (un-normalised) A rows, nullptr = A is already normalised
   };
-  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half, uint8_t* wstage) {
     const bool row_ok = row < d.M;
     const float rs = (row_ok && p.rstd) ? __ldg(p.rstd + row) : 1.f;
 #pragma unroll 1
@@ -403,7 +424,7 @@ struct EpiLse {
     const int* target;  // [M]
     float scale;
   };
-  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half) {
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half, uint8_t* wstage) {
     const bool row_ok = row < d.M;
     const int tgt = row_ok ? __ldg(p.target + row) : -1;
     constexpr float kLog2e = 1.4426950408889634f;
@@ -552,7 +573,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBN);
-      Epi::run(ep, dims, row, n_tile * kBN, n_tile, taddr, half);
+      Epi::run(ep, dims, row, n_tile * kBN, n_tile, taddr, half, smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + (warp - 4) * (32 * 80));
       tc_fence_before();
       if (is_leader) mbar_arrive(&bar_tempty[acc]); else mbar_arrive_cluster(&bar_tempty[acc], 0);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
