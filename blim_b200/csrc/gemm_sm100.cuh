@@ -49,6 +49,7 @@ struct GemmDims {
   int m_tiles;   // number of (kBM*cta_group)-row tiles
   int n_tiles;   // number of kBN-column tiles
   int sb_tiles;  // m-tiles per super-block (L2 blocking of the A operand)
+  int l2_hints;  // 1: A (the super-block slab, reused by every n-tile) is loaded evict_last, W (streamed once per super-block) evict_first
 };
 
 // tile t -> (m_tile, n_tile): super-blocks of sb_tiles m-tiles; inside a super-block m runs fastest so the CTAs that run
@@ -514,6 +515,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     // ===================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
+    const bool hints = dims.l2_hints != 0;
+    const uint64_t pol_a = hints ? l2_policy_evict_last() : 0ull, pol_b = hints ? l2_policy_evict_first() : 0ull;
     for (int t = worker; t < total_tiles; t += n_workers) {
       int m_tile, n_tile;
       tile_coords(dims, t, m_tile, n_tile);
@@ -522,7 +525,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&bar_empty[stage], phase ^ 1);
         if (is_leader) mbar_arrive_expect_tx(&bar_full[stage], Cfg::kStageBytes * kCtaGroup);
-        if constexpr (kCtaGroup == 1) {
+        if (hints) {
+          if constexpr (kCtaGroup == 1) {
+            tma_load_2d_hint(s_a + stage * Cfg::kABytes, &tm_a, &bar_full[stage], kb * kBK, m0, pol_a);
+            tma_load_2d_hint(s_b + stage * Cfg::kBBytes, &tm_b, &bar_full[stage], kb * kBK, n0, pol_b);
+          } else {
+            tma_load_2d_pair_hint(s_a + stage * Cfg::kABytes, &tm_a, &bar_full[stage], kb * kBK, m0, pol_a);
+            tma_load_2d_pair_hint(s_b + stage * Cfg::kBBytes, &tm_b, &bar_full[stage], kb * kBK, n0, pol_b);
+          }
+        } else if constexpr (kCtaGroup == 1) {
           tma_load_2d(s_a + stage * Cfg::kABytes, &tm_a, &bar_full[stage], kb * kBK, m0);
           tma_load_2d(s_b + stage * Cfg::kBBytes, &tm_b, &bar_full[stage], kb * kBK, n0);
         } else {
@@ -620,6 +631,8 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, ui
 
 struct GemmLaunchCtx {
   int num_sms = 148;
+  int l2_hints = 0;   // BLIM_GEMM_HINTS=1: eviction-priority hints on the operand loads (see GemmDims::l2_hints)
+  int sb_mb = 40;     // BLIM_GEMM_SB_MB: target size of the L2-resident A slab (MB)
   int cta_group = 1;  // 1: one CTA per tile, 2: CTA pairs (cta_group::2, 256-row tiles)
   long long launches = 0;
 };
@@ -639,10 +652,11 @@ inline cudaError_t launch_gemm_impl(GemmLaunchCtx& ctx, const __nv_bfloat16* A, 
   d.m_tiles = (M + tile_m - 1) / tile_m;
   d.n_tiles = (N + kBN - 1) / kBN;
   // keep the A super-block (sb_tiles * tile_m rows of K bf16) around 40 MB so it stays L2 resident
-  long long sb = (40ll << 20) / (static_cast<long long>(tile_m) * K * 2);
+  long long sb = (static_cast<long long>(ctx.sb_mb) << 20) / (static_cast<long long>(tile_m) * K * 2);
   if (sb < 2) sb = 2;
   if (sb > 64) sb = 64;
   d.sb_tiles = static_cast<int>(sb);
+  d.l2_hints = ctx.l2_hints;
   const int total = d.m_tiles * d.n_tiles;
   int workers = ctx.num_sms / kCtaGroup;
   if (workers > total) workers = total;
