@@ -298,7 +298,8 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
   }
   e->gemm.cta_group = cfg->gemm_cta_group == 1 ? 1 : 2;  // default: CTA pairs (cta_group::2)
   if (const char* h = getenv("BLIM_GEMM_HINTS")) e->gemm.l2_hints = atoi(h) != 0;
-  if (const char* m = getenv("BLIM_GEMM_SB_MB")) e->gemm.sb_mb = std::max(4, std::min(96, atoi(m)));
+  if (const char* m = getenv("BLIM_GEMM_SB_MB")) { e->gemm.sb_mb = std::max(4, std::min(96, atoi(m))); e->gemm.sb_auto = false; }
+  if (const char* m = getenv("BLIM_GEMM_SB_MIN")) { e->gemm.sb_min = std::max(1, std::min(8, atoi(m))); e->gemm.sb_auto = false; }
   auto bad = [&](const char* m) {
     g_create_error = m;
     delete e;

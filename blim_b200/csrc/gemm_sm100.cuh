@@ -633,6 +633,8 @@ struct GemmLaunchCtx {
   int num_sms = 148;
   int l2_hints = 0;   // BLIM_GEMM_HINTS=1: eviction-priority hints on the operand loads (see GemmDims::l2_hints)
   int sb_mb = 40;     // BLIM_GEMM_SB_MB: target size of the L2-resident A slab (MB)
+  int sb_min = 2;     // BLIM_GEMM_SB_MIN: fewest m-tiles per super-block
+  bool sb_auto = true;  // per-shape choice between the 40 MB slab and one m-tile at a time; BLIM_GEMM_SB_MB / _MIN switch it off
   int cta_group = 1;  // 1: one CTA per tile, 2: CTA pairs (cta_group::2, 256-row tiles)
   long long launches = 0;
 };
@@ -651,15 +653,24 @@ inline cudaError_t launch_gemm_impl(GemmLaunchCtx& ctx, const __nv_bfloat16* A, 
   const int tile_m = kBM * kCtaGroup;
   d.m_tiles = (M + tile_m - 1) / tile_m;
   d.n_tiles = (N + kBN - 1) / kBN;
-  // keep the A super-block (sb_tiles * tile_m rows of K bf16) around 40 MB so it stays L2 resident
+  // L2 blocking (ncu DRAM bytes per launch, profiles/ + DESIGN.md 6):
+  //  * W larger than L2 and many n-tiles (gate|up, LM head): keep an A super-block of ~40 MB L2-resident and stream W once
+  //    per super-block;
+  //  * W that fits L2 by itself (QKV, o_proj, the ViT's GEMMs), or a super-block shorter than two waves of CTAs
+  //    (down_proj: 4 m-tiles x 14 n-tiles against 74 concurrent CTA pairs, so every A panel was touched by two waves):
+  //    one m-tile at a time with n fastest -- the CTAs that share an A panel run in the same wave, A is read once.
   long long sb = (static_cast<long long>(ctx.sb_mb) << 20) / (static_cast<long long>(tile_m) * K * 2);
-  if (sb < 2) sb = 2;
+  if (sb < ctx.sb_min) sb = ctx.sb_min;
   if (sb > 64) sb = 64;
-  d.sb_tiles = static_cast<int>(sb);
-  d.l2_hints = ctx.l2_hints;
   const int total = d.m_tiles * d.n_tiles;
   int workers = ctx.num_sms / kCtaGroup;
   if (workers > total) workers = total;
+  if (ctx.sb_auto) {
+    const long long w_bytes = static_cast<long long>(N) * K * 2;
+    if (w_bytes <= (48ll << 20) || sb * d.n_tiles < 2ll * workers) sb = 1;
+  }
+  d.sb_tiles = static_cast<int>(sb);
+  d.l2_hints = ctx.l2_hints;
   auto kern = gemm_tcgen05_kernel<Epi, kCtaGroup>;
   static bool attr_set = false;  // one static per instantiation
   if (!attr_set) {
