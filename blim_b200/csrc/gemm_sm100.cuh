@@ -185,6 +185,32 @@ struct EpiStore {
   }
 };
 
+// resid[row, col .. col+31] += v for the 32 rows of a warp (lane = row), staged through the warp's shared-memory slab so that
+// every global instruction touches 8 rows x 64 contiguous bytes (full sectors) instead of 32 rows x 16 bytes: the fp32
+// residual read-modify-write is what bounds the short-K GEMMs (o_proj, the ViT's proj).  r0 = first row of the warp.
+__device__ __forceinline__ void resid_add_staged(float* __restrict__ resid, int ldo, int r0, int col, const float (&v)[32], int M, uint8_t* wstage) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float4* srow = reinterpret_cast<float4*>(wstage + lane * 80);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) srow[i] = make_float4(v[16 * h + 4 * i], v[16 * h + 4 * i + 1], v[16 * h + 4 * i + 2], v[16 * h + 4 * i + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rr = (lane >> 2) + 8 * j;
+      const float4 a = *reinterpret_cast<const float4*>(wstage + rr * 80 + (lane & 3) * 16);
+      if (r0 + rr < M) {
+        float4* g = reinterpret_cast<float4*>(resid + static_cast<size_t>(r0 + rr) * ldo + col + 16 * h + (lane & 3) * 4);
+        float4 r = *g;
+        r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+        *g = r;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // resid[row, col] += acc     (fp32 residual stream, in place).  kGroups = epilogue warpgroups that share a tile.
 template <int kGroupsT>
 struct EpiResidT {
@@ -202,21 +228,13 @@ struct EpiResidT {
       const int col = n0 + c;
       const int valid = d.N - col;
       if (valid <= 0) continue;
-      if (row_ok) {
+      if (valid >= 32) {   // warp-uniform
+        resid_add_staged(p.resid, p.ldo, row - static_cast<int>(threadIdx.x & 31), col, v, d.M, wstage);
+      } else if (row_ok) {
         float* dst = p.resid + static_cast<size_t>(row) * p.ldo + col;
-        if (valid >= 32) {
-          float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 r = d4[i];
-            r.x += v[4 * i]; r.y += v[4 * i + 1]; r.z += v[4 * i + 2]; r.w += v[4 * i + 3];
-            d4[i] = r;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < valid) dst[i] += v[i];
-        }
+        for (int i = 0; i < 32; ++i)
+          if (i < valid) dst[i] += v[i];
       }
     }
   }
@@ -241,23 +259,19 @@ struct EpiResidBias {
       const int col = n0 + c;
       const int valid = d.N - col;
       if (valid <= 0) continue;
-      if (row_ok) {
-        float* dst = p.resid + static_cast<size_t>(row) * p.ldo + col;
-        if (valid >= 32) {
-          float4* d4 = reinterpret_cast<float4*>(dst);
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+      if (valid >= 32) {   // warp-uniform
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 r = d4[i];
-            const float4 b = __ldg(b4 + i);
-            r.x += v[4 * i] + b.x; r.y += v[4 * i + 1] + b.y; r.z += v[4 * i + 2] + b.z; r.w += v[4 * i + 3] + b.w;
-            d4[i] = r;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < valid) dst[i] += v[i] + __ldg(p.bias + col + i);
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = __ldg(b4 + i);
+          v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
         }
+        resid_add_staged(p.resid, p.ldo, row - static_cast<int>(threadIdx.x & 31), col, v, d.M, wstage);
+      } else if (row_ok) {
+        float* dst = p.resid + static_cast<size_t>(row) * p.ldo + col;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < valid) dst[i] += v[i] + __ldg(p.bias + col + i);
       }
     }
   }
