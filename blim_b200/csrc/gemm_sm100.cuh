@@ -124,6 +124,27 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+// out[row, col .. col+31] = bf16(v) for the 32 rows of a warp (lane = row).  Row-per-thread stores scatter every warp
+// instruction over 32 rows (32 half-used sectors); the warp's 32 x 64 B go through its shared-memory slab instead and
+// are stored 8 rows x 64 contiguous bytes per instruction.  r0 = first row of the warp.
+__device__ __forceinline__ void store_tile32_bf16_staged(__nv_bfloat16* __restrict__ out, int ldo, int r0, int col, const float (&v)[32], int M,
+                                                         uint8_t* wstage) {
+  const int lane = threadIdx.x & 31;
+  uint4* srow = reinterpret_cast<uint4*>(wstage + lane * 80);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    srow[i] = make_uint4(pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                         pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int rr = (lane >> 2) + 8 * j;
+    const uint4 val = *reinterpret_cast<const uint4*>(wstage + rr * 80 + (lane & 3) * 16);
+    if (r0 + rr < M) *reinterpret_cast<uint4*>(out + static_cast<size_t>(r0 + rr) * ldo + col + (lane & 3) * 8) = val;
+  }
+  __syncwarp();
+}
+
 // Every epilogue gets: this thread's global row (may be >= M: loads from TMEM still have to be executed warp-uniformly,
 // only the global-memory side is predicated), the tile's first column n0, the TMEM address of (its lane, column 0
 // of the accumulator stage) and `half` (0/1): which half of the tile's work this epilogue warpgroup owns.
@@ -157,24 +178,7 @@ struct EpiStore {
       }
       if constexpr (sizeof(OutT) == 2) {
         if (valid >= 32) {   // warp-uniform
-          // Row-per-thread stores scatter every warp instruction over 32 rows (32 half-used sectors).  Stage the warp's
-          // 32 x 64 B through shared memory instead and store 8 rows x 64 contiguous bytes per instruction.
-          const int lane = threadIdx.x & 31;
-          uint4* srow = reinterpret_cast<uint4*>(wstage + lane * 80);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            srow[i] = make_uint4(pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                 pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-          __syncwarp();
-          const int r0 = row - lane;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int rr = (lane >> 2) + 8 * j;
-            const uint4 val = *reinterpret_cast<const uint4*>(wstage + rr * 80 + (lane & 3) * 16);
-            if (r0 + rr < d.M)
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(r0 + rr) * p.ldo + col + (lane & 3) * 8) = val;
-          }
-          __syncwarp();
+          store_tile32_bf16_staged(reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, row - static_cast<int>(threadIdx.x & 31), col, v, d.M, wstage);
         } else if (row_ok) {
           store_row32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col, v, valid);
         }
@@ -424,7 +428,7 @@ struct EpiSwiglu {
         const float x = g[i] * rs;
         g[i] = (x / (1.0f + __expf(-x))) * (u[i] * rs);
       }
-      if (row_ok) store_row32_bf16(p.act + static_cast<size_t>(row) * p.ldo + n_tile * 128 + c, g, 32);
+      store_tile32_bf16_staged(p.act, p.ldo, row - static_cast<int>(threadIdx.x & 31), n_tile * 128 + c, g, d.M, wstage);
     }
   }
 };
