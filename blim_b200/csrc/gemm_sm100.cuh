@@ -426,7 +426,7 @@ struct EpiSwiglu {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const float x = g[i] * rs;
-        g[i] = (x / (1.0f + __expf(-x))) * (u[i] * rs);
+        g[i] = x * fast_rcp(1.0f + fast_exp2(-1.4426950408889634f * x)) * (u[i] * rs);   // silu(x) * up: one MUFU.EX2 + one MUFU.RCP
       }
       store_tile32_bf16_staged(p.act, p.ldo, row - static_cast<int>(threadIdx.x & 31), n_tile * 128 + c, g, d.M, wstage);
     }
