@@ -36,6 +36,9 @@ def _nvcc():
     raise RuntimeError("nvcc not found: the BLiM B200 engine cannot be built (there is no CPU fallback)")
 
 
+NVCC_FLAGS += os.environ.get("BLIM_NVCC_EXTRA", "").split()   # e.g. -DBLIM_EXACT_SILU for numerical A/B builds
+
+
 def _digest():
     h = hashlib.sha256()
     for f in SOURCES + HEADERS:

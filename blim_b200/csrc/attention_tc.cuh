@@ -884,18 +884,21 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
 //     bar_sfree[2]  every thread holds its S(c) row    (256 arrivals)        -> issue warp may overwrite that accumulator
 //     bar_p         P(c) in shared memory, O rescaled  (256 arrivals)        -> issue warp starts Oc = P V
 //     bar_o[2]      Oc of chunk c complete             (tcgen05.commit)      -> P tile / V stage free, O readable
-// and among themselves through a 256-thread named barrier for the row-maximum exchange.  S(c+1) = Q K(c+1)^T is issued as
+// and among themselves only pairwise: the two threads of a row sit in warps w and w + 4 (same TMEM lane quadrant), which
+// exchange the row maximum through shared memory and a 64-thread named barrier of their own (ids 1..4).  S(c+1) = Q K(c+1)^T is issued as
 // soon as S(c) completes, i.e. it runs under the softmax of chunk c.  head_dim 64 has room for TWO P tiles: P(c+1) is
 // written while Oc(c) = P(c) V(c) is still running, and a thread waits for Oc(c-1) only when it must rescale O.
 constexpr int kTc4Threads = 288;
 
 template <int DH>
 constexpr int attn_tc4_smem_bytes() {
-  // Q (DH/64 x 16 KB) + 2 x K + 2 x V (DH/64 x 8 KB each) + P (16 KB; two for head_dim 64) + max exchange (512 B) + barriers (96 B)
-  return (DH / 64) * 16384 + 4 * (DH / 64) * 8192 + (DH == 64 ? 2 : 1) * 16384 + 512 + 96;
+  // Q (DH/64 x 16 KB) + 2 x K + 2 x V (DH/64 x 8 KB each) + P (16 KB; two for head_dim 64) + max exchange (512 B; two
+  // for head_dim 64) + barriers (96 B)
+  return (DH / 64) * 16384 + 4 * (DH / 64) * 8192 + (DH == 64 ? 2 : 1) * (16384 + 512) + 96;
 }
 
-__device__ __forceinline__ void softmax_group_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// barrier of the two warps (w, w + 4) that share TMEM lane quadrant q = w & 3
+__device__ __forceinline__ void softmax_pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
 
 template <int DH>
 __global__ void __launch_bounds__(kTc4Threads, 2)
@@ -906,13 +909,14 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   constexpr float kGrow = 8.0f;
   constexpr bool kPDouble = DH == 64;
   constexpr int kPBytes = (kPDouble ? 2 : 1) * 16384;
+  constexpr int kMxBytes = (kPDouble ? 2 : 1) * 512;
   extern __shared__ __align__(1024) uint8_t smem_tc4[];
   uint8_t* s_q = smem_tc4;
   uint8_t* s_k = s_q + kSub * 16384;           // two stages
   uint8_t* s_v = s_k + 2 * kSub * 8192;        // two stages
   uint8_t* s_p = s_v + 2 * kSub * 8192;
   __nv_bfloat16* s_mx = reinterpret_cast<__nv_bfloat16*>(s_p + kPBytes);   // [2][128] row maxima of the two half-row threads
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + kPBytes + 512);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + kPBytes + kMxBytes);
   uint64_t* bar_s = bars;        // [2]
   uint64_t* bar_k = bars + 2;    // [2]
   uint64_t* bar_v = bars + 4;    // [2]
@@ -1126,10 +1130,11 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
     }
     tc_fence_before();
     mbar_arrive(&bar_sfree[c & 1]);                  // this thread's S(c) values are in registers
-    s_mx[half * 128 + r] = __float2bfloat16(cmax);   // both threads of the row use the same (bf16-rounded) pair of maxima
-    softmax_group_sync();   // [A] maxima visible
-    const float cmax_s = fmaxf(__bfloat162float(s_mx[r]), __bfloat162float(s_mx[128 + r])) * p.scale_log2;
-    softmax_group_sync();   // [A'] maxima read: the exchange buffer may be overwritten by the next chunk
+    __nv_bfloat16* mx = s_mx + (kPDouble ? (c & 1) * 256 : 0);
+    mx[half * 128 + r] = __float2bfloat16(cmax);   // both threads of the row use the same (bf16-rounded) pair of maxima
+    softmax_pair_sync(warp & 3);   // [A] the partner's maximum is visible
+    const float cmax_s = fmaxf(__bfloat162float(mx[r]), __bfloat162float(mx[128 + r])) * p.scale_log2;
+    if constexpr (!kPDouble) softmax_pair_sync(warp & 3);   // [A'] single exchange buffer: read before the next chunk overwrites it
 
     if constexpr (!kPDouble) {
       if (c > 0) {
@@ -1198,7 +1203,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   tc_fence_after();
   float* s_l = reinterpret_cast<float*>(s_p);
   s_l[half * 128 + r] = l_part;
-  softmax_group_sync();
+  softmax_pair_sync(warp & 3);
   const float l = s_l[r] + s_l[128 + r];
   const float inv = l > 0.f ? 1.0f / l : 0.f;
   __nv_bfloat16* dst = p.o + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH + half * (DH / 2);

@@ -426,7 +426,11 @@ struct EpiSwiglu {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const float x = g[i] * rs;
+#ifdef BLIM_EXACT_SILU
+        g[i] = (x / (1.0f + __expf(-x))) * (u[i] * rs);
+#else
         g[i] = x * fast_rcp(1.0f + fast_exp2(-1.4426950408889634f * x)) * (u[i] * rs);   // silu(x) * up: one MUFU.EX2 + one MUFU.RCP
+#endif
       }
       store_tile32_bf16_staged(p.act, p.ldo, row - static_cast<int>(threadIdx.x & 31), n_tile * 128 + c, g, d.M, wstage);
     }
@@ -471,8 +475,13 @@ struct EpiLse {
       }
       const float m_new = fmaxf(m_run, cm);
       float s = 0.f;
+      const float m_l2 = m_new * kLog2e;
 #pragma unroll
+#ifdef BLIM_EXACT_LSE
       for (int i = 0; i < 32; ++i) s += exp2f((v[i] - m_new) * kLog2e);
+#else
+      for (int i = 0; i < 32; ++i) s += fast_exp2(fmaf(v[i], kLog2e, -m_l2));   // one FFMA + one MUFU.EX2 per logit
+#endif
       s_run = s_run * exp2f((m_run - m_new) * kLog2e) + s;
       m_run = m_new;
     }
