@@ -172,6 +172,12 @@ class Engine:
                 ids, labels = ids[mask], labels[mask]
         off = np.zeros(len(ids_list) + 1, dtype=np.int64)
         np.cumsum(lens, out=off[1:])
+        # token counts per text for the multi-GPU load balancer (retrieval.balanced_owner_ranks)
+        seg = np.repeat(np.arange(len(lens)), lens)
+        if not hasattr(self, "text_lens"):
+            self.text_lens = {}
+        self.text_lens[which] = {"total": lens.astype(np.float64),
+                                 "scored": np.bincount(seg, weights=(labels != -100), minlength=len(lens)).astype(np.float64)}
         ids, labels = np.ascontiguousarray(ids), np.ascontiguousarray(labels)
         assert len(ids) == len(labels) == off[-1]
         self._check(self.lib.blim_set_texts(self.h, which, ids.ctypes.data_as(ctypes.c_void_p), labels.ctypes.data_as(ctypes.c_void_p),

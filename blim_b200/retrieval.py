@@ -131,6 +131,43 @@ class PairPlan:
         self.t2v_np = (packed[2 * nu + 2 * na:2 * nu + 2 * na + nb], packed[2 * nu + 2 * na + nb:])
 
 
+def balanced_owner_ranks(owner, pair_cost, owner_base_cost, world):
+    """Which rank scores which prefix owner: owners sorted by estimated decoder tokens (shared prefix once + the suffix
+    tokens of all their pairs), largest first, each to the currently lightest rank (LPT).  Deterministic, so every rank
+    derives the same assignment from the plan.  Returns rank_of_owner indexed by owner id."""
+    n_owner = int(owner.max()) + 1 if len(owner) else 0
+    cost = np.bincount(owner, weights=pair_cost, minlength=n_owner).astype(np.float64)
+    used = cost > 0
+    cost = cost + np.where(used, owner_base_cost, 0.0)
+    order = np.argsort(-cost, kind="stable")
+    load = np.zeros(world)
+    rank_of = np.zeros(n_owner, dtype=np.int64)
+    for o in order:
+        if not used[o]:
+            break
+        r = int(np.argmin(load))
+        rank_of[o] = r
+        load[r] += cost[o]
+    return rank_of
+
+
+def _shard_costs(eng, kind, pv, pt):
+    """(owner ids, per-pair suffix tokens, per-owner prefix tokens) for the scheduler's four run shapes (csrc/engine.cu)."""
+    lens = getattr(eng, "text_lens", None)
+    if not lens or TEXTS_VTG not in lens or TEXTS_TVG not in lens:
+        lens = None
+    n_vis = getattr(eng, "n_clips", 4) * 64
+    cap = lens[TEXTS_VTG]["scored"] if lens else None
+    tlen = lens[TEXTS_TVG]["total"] if lens else None
+    if kind == VTG:          # owner = video: prefix (header + visual rows + prompt) once, one caption suffix per pair
+        return pv, (cap[pt] if lens else np.full(len(pv), 14.0)), n_vis + 26.0
+    if kind == VTG_PRIOR:    # owner = text: one suffix per distinct text, the 26-token prefix is shared by everyone
+        return pt, (cap[pt] / 16.0 if lens else np.ones(len(pt))), 0.0
+    if kind == TVG:          # owner = text: text prefix once, n_clips - 1 visual rows per pair
+        return pt, np.full(len(pt), 3.0), (tlen if lens else 45.0)
+    return pv, np.full(len(pv), 4.0), 0.0   # TVG_PRIOR, owner = video
+
+
 def score_all(model, plan: PairPlan, cpn=True, full=True, distributed=False):
     """Scores every term evaluation() needs on the deduplicated pair set.  Multi-GPU: the pairs are sharded by the id
     that owns the shared prefix (each video / text prefix is prefilled on exactly one rank); every rank derives all
@@ -145,9 +182,13 @@ def score_all(model, plan: PairPlan, cpn=True, full=True, distributed=False):
     def run(kind, pv, pt):
         if world == 1:
             return eng.score_pairs(kind, pv, pt)
-        # shard by the id that owns the shared prefix: video for VTG / TVG prior, text for VTG prior / TVG
-        owner = pv if kind in (VTG, TVG_PRIOR) else pt
-        shards = [np.nonzero(owner % world == r)[0] for r in range(world)]
+        # shard by the id that owns the shared prefix (video for VTG / TVG prior, text for VTG prior / TVG), owners
+        # assigned to ranks by estimated decoder tokens so that the ranks finish together
+        owner, pair_cost, base = _shard_costs(eng, kind, pv, pt)
+        base = base[: int(owner.max()) + 1] if isinstance(base, np.ndarray) else base
+        rank_of = balanced_owner_ranks(owner, pair_cost, base, world)
+        pair_rank = rank_of[owner]
+        shards = [np.nonzero(pair_rank == r)[0] for r in range(world)]
         width = max(len(x) for x in shards)
         buf = torch.zeros(width, dtype=torch.float32, device=eng.device)
         mine = shards[rank]

@@ -118,6 +118,23 @@ def test_score_all_sharded_over_two_ranks_matches_single(tmp_path):
             assert torch.equal(a[k], b[k]), k
 
 
+def test_balanced_owner_ranks_lpt():
+    """Multi-GPU sharding: every owner on exactly one rank, loads within one largest item of each other, deterministic."""
+    from blim_b200.retrieval import balanced_owner_ranks
+    rng = np.random.default_rng(0)
+    owner = rng.integers(0, 200, size=3000)
+    owner = owner[owner % 7 != 3]                      # some owner ids never occur
+    cost = rng.integers(3, 40, size=len(owner)).astype(np.float64)
+    for world in (2, 3, 8):
+        rank_of = balanced_owner_ranks(owner, cost, 282.0, world)
+        assert np.array_equal(rank_of, balanced_owner_ranks(owner, cost, 282.0, world))
+        per_owner = np.bincount(owner, weights=cost, minlength=len(rank_of)) + np.where(np.bincount(owner, minlength=len(rank_of)) > 0, 282.0, 0.0)
+        load = np.bincount(rank_of, weights=per_owner, minlength=world)
+        assert load.max() - load.min() <= per_owner.max()
+        naive = np.bincount(np.arange(len(rank_of)) % world, weights=per_owner, minlength=world)
+        assert load.max() <= naive.max() + 1e-9          # never worse than the round-robin it replaces
+
+
 def test_algorithmic_flops_matches_survey_order_of_magnitude():
     """C2 needs ~13.5 PFLOP (~0.42 TFLOP per pair)."""
     import bench
