@@ -52,6 +52,7 @@ struct AttnParamsTc {
   int n_q, n_kv, group;
   float scale_log2;
   int q_stride;               // elements between the Q rows of consecutive tokens (n_q, or 3 * n_q for a packed [Q|K|V] buffer)
+  int n_works, n_kv_heads;    // filled by launch_attention_tc (the persistent kernel walks items = works x KV heads)
 };
 
 constexpr int kTcKeys = 64;       // keys per chunk
@@ -589,6 +590,296 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
       }
     }
   }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc<1>(tmem, kTcTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ v2p: persistent v2
+// The scoring path's work items are short (282 prefix keys + a few own keys = 5-6 chunks), so what a v2 CTA does once --
+// barrier initialisation, TMEM allocation, tensor-map prefetch, the CTA launch itself -- is a large part of its life.
+// v2p launches two CTAs per SM once and lets each walk over work items (item = work x KV head, consecutive items share the
+// prefix K/V in L2); the mbarrier phases simply keep counting chunks across items (g = chunks done so far + c).
+template <int DH>
+__global__ void __launch_bounds__(kTc2Threads, 2)
+attention_tc2p_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_constant__ CUtensorMap tm_va,
+                     const __grid_constant__ CUtensorMap tm_kb, const __grid_constant__ CUtensorMap tm_vb, const AttnParamsTc p) {
+  constexpr int kSub = DH / 64;
+  constexpr uint32_t kChunkBytes = kSub * 8192;
+  constexpr float kGrow = 8.0f;  // lazy rescale threshold (log2 units): P stays below 2^8
+  extern __shared__ uint8_t smem_raw_tc[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* s_q = smem;
+  uint8_t* s_k = s_q + kSub * 16384;
+  uint8_t* s_v = s_k + kSub * 8192;          // two stages
+  uint8_t* s_p = s_v + 2 * kSub * 8192;
+  __shared__ uint64_t bar_s, bar_o, bar_k, bar_v[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_x[2][128];              // per-row exchange between the two threads of a row (max, then sum)
+
+  AttnWorkTc w;
+  int kvh = 0, g0 = 0, n_a = 0, n_chunks = 0;   // per item; g0 = chunks of the items this CTA has finished
+  const int G = p.group;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid & 127, half = tid >> 7;
+  // Warp 0 issues every TMA / tcgen05.mma with uniform control flow (all 32 lanes walk the issue code, so addresses and
+  // descriptors are computed once in uniform registers) and only the issuing instruction is predicated on the elected lane:
+  // the issue work sits on the CTA's critical path (everyone waits for warp 0 at the barriers).
+  const bool lead = warp == 0 ? elect_one() != 0 : false;
+
+  if (tid == 0) {
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_o, 1);
+    mbar_init(&bar_k, 1);
+    mbar_init(&bar_v[0], 1);
+    mbar_init(&bar_v[1], 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_ka);
+    tma_prefetch_desc(&tm_va);
+    tma_prefetch_desc(&tm_kb);
+    tma_prefetch_desc(&tm_vb);
+  }
+  if (warp == 0) tmem_alloc<1>(&tmem_slot, kTcTmemCols);
+  const int tok_local = r / G, head = r - tok_local * G;
+
+  auto chunk_keys = [&](int c, int& nk, int& key0, bool& own, int& tm_row) {
+    if (c < n_a) {
+      own = false;
+      key0 = c * kTcKeys;
+      nk = min(kTcKeys, w.a_len - key0);
+      tm_row = p.a_row0 + w.a_start + key0;
+    } else {
+      own = true;
+      key0 = w.kb0 + (c - n_a) * kTcKeys;
+      nk = min(kTcKeys, w.tok0 + w.n_tok - key0);
+      tm_row = p.b_row0 + key0 + w.b_off;
+    }
+  };
+  auto stage = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tm_row) {   // warp 0
+    if (lead) {
+      mbar_arrive_expect_tx(bar, kChunkBytes);
+#pragma unroll
+      for (int sub = 0; sub < kSub; ++sub) tma_load_2d(dst + sub * 8192, tm, bar, kvh * DH + sub * 64, tm_row);
+    }
+  };
+  auto stage_k = [&](int c) {
+    int nk, key0, row; bool own;
+    chunk_keys(c, nk, key0, own, row);
+    stage(s_k, own ? &tm_kb : &tm_ka, &bar_k, row);
+  };
+  auto stage_v = [&](int c) {
+    int nk, key0, row; bool own;
+    chunk_keys(c, nk, key0, own, row);
+    stage(s_v + ((g0 + c) & 1) * kSub * 8192, own ? &tm_vb : &tm_va, &bar_v[(g0 + c) & 1], row);
+  };
+  auto issue_s = [&](int c, uint32_t tmem) {   // S = Q K^T of chunk c (warp 0)
+    int nk, key0, row; bool own;
+    chunk_keys(c, nk, key0, own, row);
+    const int nk16 = (nk + 15) & ~15;
+    mbar_wait(&bar_k, static_cast<uint32_t>((g0 + c) & 1));
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16_ex(128, nk16, 0);
+    if (lead) {
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        const uint64_t da = make_smem_desc_sw128(smem_u32(s_q) + (kk >> 2) * 16384 + (kk & 3) * 32);
+        const uint64_t db = make_smem_desc_sw128(smem_u32(s_k) + (kk >> 2) * 8192 + (kk & 3) * 32);
+        umma_bf16<1>(tmem, da, db, idesc, kk != 0 ? 1u : 0u);
+      }
+      umma_commit(&bar_s);
+    }
+    __syncwarp();
+  };
+
+  tc_fence_before();
+  __syncthreads();   // barriers initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  const uint32_t t_s = t_row + half * 32;                 // this thread's 32 S columns
+  const uint32_t t_o = t_row + 64 + half * (DH / 2);      // this thread's DH/2 O columns
+  const int n_items = p.n_works * p.n_kv_heads;
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  w = p.works[item % p.n_works];
+  kvh = item / p.n_works;
+  const bool row_ok = tok_local < w.n_tok;
+  const int rt = w.tok0 + (row_ok ? tok_local : 0);
+  const int seq_lo = (row_ok && p.tok_seq_start != nullptr) ? __ldg(p.tok_seq_start + rt) : 0;
+  {
+    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.q_stride + (kvh * G + head) * DH;
+#pragma unroll
+    for (int cc = 0; cc < DH / 16; ++cc) {
+      const int c = half * (DH / 16) + cc;
+      cp_async16(s_q + (c >> 3) * 16384 + sw128_offset(r, (c & 7) * 8), src + c * 8, row_ok ? 16 : 0);
+    }
+    cp_async_commit();
+  }
+  n_a = (w.a_len + kTcKeys - 1) / kTcKeys;
+  n_chunks = n_a + (w.tok0 + w.n_tok - w.kb0 + kTcKeys - 1) / kTcKeys;
+  cp_async_wait<0>();
+  fence_proxy_async();
+  __syncthreads();   // Q staged; every thread is done with the previous item (its O rows are read, its exchange slots are free)
+  if (warp == 0) {
+    stage_k(0);
+    stage_v(0);
+    if (n_chunks > 1) stage_v(1);
+    issue_s(0, tmem);
+  }
+  float m_ref = -INFINITY, l_part = 0.f;
+
+  for (int c = 0; c < n_chunks; ++c) {
+    int nk, key0, tm_row_unused; bool own;
+    chunk_keys(c, nk, key0, own, tm_row_unused);
+    const int nk16 = (nk + 15) & ~15;
+
+    mbar_wait(&bar_s, static_cast<uint32_t>((g0 + c) & 1));
+    __syncwarp();   // the tcgen05.ld / .st below are warp-collective: reconverge after the per-lane spin
+    tc_fence_after();
+    // ---- this thread's 32 keys of the row
+    float sv[32];
+    if (half * 32 < nk16) {   // warp-uniform
+      uint32_t raw[32];
+      tmem_ld32(t_s, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(raw[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sv[i] = 0.f;
+    }
+    float cmax = -INFINITY;
+    if (!own && nk == kTcKeys) {   // CTA-uniform fast path: a full chunk of the shared prefix, every key visible
+#pragma unroll
+      for (int i = 0; i < 32; ++i) cmax = fmaxf(cmax, sv[i]);
+    } else {
+      int j_lo = 0, j_hi = nk - 1;
+      if (own) {
+        j_lo = max(0, seq_lo - key0);
+        j_hi = min(nk - 1, rt - key0);
+      }
+      // visible keys among this thread's 32 as a bit mask: [j_lo, j_hi] clipped to the half's window
+      const int lo = max(j_lo - half * 32, 0), hi = min(j_hi - half * 32, 31);
+      uint32_t vmask = (hi >= lo) ? ((0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo)) : 0u;
+      if (own && p.key_valid != nullptr && vmask != 0u) {
+        const uint8_t* kv = p.key_valid + key0 + half * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (((vmask >> i) & 1u) && kv[i] == 0) vmask &= ~(1u << i);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float val = ((vmask >> i) & 1u) ? sv[i] : -INFINITY;
+        sv[i] = val;
+        cmax = fmaxf(cmax, val);
+      }
+    }
+    s_x[half][r] = cmax;
+    tc_fence_before();
+    __syncthreads();   // [A] every S(c) value is in registers: the S columns and the K buffer are free
+    if (warp == 0 && c + 1 < n_chunks) stage_k(c + 1);
+    const float cmax_s = fmaxf(s_x[0][r], s_x[1][r]) * p.scale_log2;   // -inf * positive = -inf
+
+    // ---- Oc = P V of the previous chunk has to be complete before P / O are touched
+    if (c > 0) {
+      mbar_wait(&bar_o, static_cast<uint32_t>((g0 + c - 1) & 1));
+      tc_fence_after();
+      if (warp == 0 && c + 1 < n_chunks) stage_v(c + 1);   // its buffer was read by chunk c-1
+      __syncwarp();
+    }
+    // ---- lazy rescale of O (TMEM) and of the running sum
+    float corr = 1.f;
+    bool grow = false;
+    if (c == 0) {
+      m_ref = cmax_s;
+    } else if (cmax_s > m_ref + kGrow) {
+      grow = true;
+      corr = exp2f(m_ref - cmax_s);   // 0 when nothing was visible before
+      m_ref = cmax_s;
+      l_part *= corr;
+    }
+    if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll
+      for (int h = 0; h < DH / 64; ++h) {
+        uint32_t raw[32];
+        tmem_ld32(t_o + h * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
+        tmem_st32(t_o + h * 32, raw);
+      }
+      tmem_st_wait();
+    }
+    // ---- P for this thread's 32 keys
+    const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+    float csum = 0.f;
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p0 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
+        const float p1 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
+        csum += p0 + p1;
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+        pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      if (half * 32 + j8 * 8 < nk16) *reinterpret_cast<uint4*>(s_p + sw128_offset(r, half * 32 + j8 * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    l_part += csum;
+
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();   // [B] P written, O rescaled
+    if (warp == 0) {
+      mbar_wait(&bar_v[(g0 + c) & 1], static_cast<uint32_t>(((g0 + c) >> 1) & 1));
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16_ex(128, DH, 1);
+      const uint32_t v_base = smem_u32(s_v) + ((g0 + c) & 1) * kSub * 8192;
+      if (lead) {
+        for (int kk = 0; kk < nk16 / 16; ++kk) {
+          const uint64_t da = make_smem_desc_sw128(smem_u32(s_p) + kk * 32);
+          const uint64_t db = make_smem_desc_raw(v_base + kk * 2048, 8192, 1024);
+          umma_bf16<1>(tmem + 64, da, db, idesc, (c > 0 || kk != 0) ? 1u : 0u);
+        }
+        umma_commit(&bar_o);
+      }
+      __syncwarp();
+      if (c + 1 < n_chunks) issue_s(c + 1, tmem);
+    }
+  }
+
+  // ---- O / l -> bf16
+  mbar_wait(&bar_o, static_cast<uint32_t>((g0 + n_chunks - 1) & 1));
+  __syncwarp();
+  tc_fence_after();
+  s_x[half][r] = l_part;
+  __syncthreads();
+  const float l = s_x[0][r] + s_x[1][r];
+  const float inv = l > 0.f ? 1.0f / l : 0.f;
+  __nv_bfloat16* dst = p.o + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH + half * (DH / 2);
+#pragma unroll
+  for (int h = 0; h < DH / 64; ++h) {
+    uint32_t raw[32];
+    tmem_ld32(t_o + h * 32, raw);
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(raw[c8 * 8 + 2 * e]) * inv, __uint_as_float(raw[c8 * 8 + 2 * e + 1]) * inv);
+          pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        *reinterpret_cast<uint4*>(dst + h * 32 + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+  g0 += n_chunks;
+  }   // items
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1362,6 +1653,38 @@ inline cudaError_t launch_attention_tc(const AttnTcMaps& m, const AttnParamsTc& 
                   : head_dim == 64 ? launch_attention_tc3_impl<64>(m, p, grid, stream) : cudaErrorInvalidValue;
     if (e != cudaErrorLaunchOutOfResources) return e;
     version = 2;  // two CTAs per SM do not fit: the single-buffered kernel is the better choice
+  }
+  if (version == 5) {   // persistent v2
+    AttnParamsTc pp = p;
+    pp.n_works = n_works;
+    pp.n_kv_heads = n_kv_heads;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm = 148;
+    }
+    const int items = n_works * n_kv_heads;
+    dim3 pgrid(static_cast<unsigned>(std::min(items, 2 * n_sm)));
+    if (head_dim == 128) {
+      static bool set = false;
+      if (!set) {
+        cudaError_t e = cudaFuncSetAttribute(attention_tc2p_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc2_smem_bytes<128>());
+        if (e != cudaSuccess) return e;
+        set = true;
+      }
+      attention_tc2p_kernel<128><<<pgrid, kTc2Threads, attn_tc2_smem_bytes<128>(), stream>>>(m.ka, m.va, m.kb, m.vb, pp);
+    } else if (head_dim == 64) {
+      static bool set = false;
+      if (!set) {
+        cudaError_t e = cudaFuncSetAttribute(attention_tc2p_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc2_smem_bytes<64>());
+        if (e != cudaSuccess) return e;
+        set = true;
+      }
+      attention_tc2p_kernel<64><<<pgrid, kTc2Threads, attn_tc2_smem_bytes<64>(), stream>>>(m.ka, m.va, m.kb, m.vb, pp);
+    } else {
+      return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
   }
   if (version == 2) {
     if (head_dim == 128) return launch_attention_tc2_impl<128>(m, p, grid, stream);

@@ -146,7 +146,7 @@ struct blim_engine {
   DevBuf vis_in, d_vis_idx;  // projector input staging for non-contiguous video sets (gathered feature rows + their indices)
   DevBuf d_tok_slot, d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
   bool attn_tc = true;  // tcgen05 attention (BLIM_ATTN=mma selects the mma.sync kernel, tc1 the first tcgen05 kernel)
-  int attn_tc_version = 2;
+  int attn_tc_version = 5;  // 5 = persistent v2 (default), 2 = v2, 1 / 3 / 4 = A/B variants (BLIM_ATTN=tc2p|tc2|tc1|tc3|tc4)
   uint8_t* arena = nullptr;  // pinned staging arena for scheduler metadata (see upload())
   size_t arena_cap = 0, arena_off = 0;
   bool arena_disabled = false;
@@ -290,7 +290,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
   {
     const char* a = getenv("BLIM_ATTN");
     e->attn_tc = !(a && std::string(a) == "mma");
-    e->attn_tc_version = (a && std::string(a) == "tc1") ? 1 : (a && std::string(a) == "tc3") ? 3 : (a && std::string(a) == "tc4") ? 4 : 2;
+    e->attn_tc_version = (a && std::string(a) == "tc1") ? 1 : (a && std::string(a) == "tc3") ? 3 : (a && std::string(a) == "tc4") ? 4 : (a && std::string(a) == "tc2") ? 2 : 5;
     const char* rs = getenv("BLIM_ROOT");
     e->root_share = !(rs && std::string(rs) == "0");
     const char* f = getenv("BLIM_FUSE_NORM");
@@ -725,7 +725,7 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
       maps.vb = to_prefix_cache ? e->tm_vp : e->tm_vown;
       ap.key_valid = run.any_invalid ? e->d_key_valid.as<uint8_t>() : nullptr;
       ap.tok_seq_start = e->d_seq_start.as<int>(); ap.works = e->d_works.as<AttnWorkTc>();
-      ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G; ap.scale_log2 = scale_log2; ap.q_stride = e->NQ;
+      ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G; ap.scale_log2 = scale_log2; ap.q_stride = e->NQ; ap.n_works = n_works; ap.n_kv_heads = e->NKV;
       r = launch_attention_tc(maps, ap, n_works, e->NKV, e->DH, st, e->attn_tc_version);
     } else {
       AttnParams ap;

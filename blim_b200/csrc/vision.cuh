@@ -634,6 +634,7 @@ static int vis_encode(blim_vision* v, const void* frames, int dtype, int n_frame
   ap.n_q = C; ap.n_kv = C; ap.group = 1;
   ap.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(v->DH));   // qk_scale = head_dim^-0.5 (vision_tower_builder.py:77)
   ap.q_stride = 3 * C;
+  ap.n_works = v->n_works; ap.n_kv_heads = v->NH;
 
   for (int l = 0; l < v->NL; ++l) {
     const VisBlockW& w = v->blocks[l];
