@@ -120,8 +120,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
   p = fmaf(p, t, 0.254829592f);
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
-  const float erf_abs = fmaf(-p * t, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float h = 0.5f * p * t * e;          // 0.5 * erfc(|z|) = Phi(-|x|)
+  return x * (x >= 0.f ? 1.0f - h : h);      // x * Phi(x)
 }
 
 // out[row, col .. col+31] = bf16(v) for the 32 rows of a warp (lane = row).  Row-per-thread stores scatter every warp
@@ -168,9 +168,18 @@ struct EpiStore {
       const int valid = d.N - col;
       if (valid <= 0) continue;  // warp-uniform
       if constexpr (kBias) {
+        if (valid >= 32) {   // warp-uniform: whole 32-column step in range
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < valid) v[i] += __ldg(p.bias + col + i);
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(b4 + i);
+            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < valid) v[i] += __ldg(p.bias + col + i);
+        }
       }
       if constexpr (kGelu) {
 #pragma unroll

@@ -118,6 +118,22 @@ def test_score_all_sharded_over_two_ranks_matches_single(tmp_path):
             assert torch.equal(a[k], b[k]), k
 
 
+def test_extractor_fails_loudly_without_gpu_and_chunks_cover_the_list():
+    from blim_b200 import extract
+    from blim_b200 import vision as V
+    if not torch.cuda.is_available():
+        with pytest.raises(V.VisionError):
+            V.VisionEncoder(V.VisionConfig.tiny())
+    for n, k in ((10, 3), (7, 7), (5, 1), (1000, 8)):      # extract.py:79-85
+        spans = [extract.chunk_bounds(n, k, i) for i in range(k)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(k - 1))
+    assert extract.video_id("/x/movie_a/clip_0001.avi", "LSMDC") == "clip_0001" and extract.video_id("/x/video7.mp4", "MSRVTT") == "video7"
+    cfg = V.VisionConfig.umt_l(448)
+    assert cfg.num_layers == 23 and cfg.tokens_per_clip == 3136 and cfg.mlp_hidden_size == 4096
+    assert len(V.param_shapes(cfg)) == 2 + 13 * 23 + 2
+
+
 def test_balanced_owner_ranks_lpt():
     """Multi-GPU sharding: every owner on exactly one rank, loads within one largest item of each other, deterministic."""
     from blim_b200.retrieval import balanced_owner_ranks
