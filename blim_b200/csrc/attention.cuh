@@ -33,6 +33,8 @@ struct AttnSeq {
   int a_start;  // first prefix key row in k_a / v_a
   int a_len;
   int b_start;  // first own key row in k_b / v_b (its q_len tokens are consecutive rows)
+  int unit;     // scheduling unit (video / text) the sequence belongs to: attention tiles never stack sequences of different
+                // units, so a unit's numbers do not depend on which other units share its run (multi-GPU sharding, batching)
 };
 // 64 stacked rows of the sequences seq_first .. seq_first + n_seq - 1 (all sharing a_start / a_len); the block starts at
 // row `row_first` of sequence seq_first (row = token * G + head_in_group).

@@ -1533,7 +1533,7 @@ inline void build_attn_works_tc(const AttnSeq* seqs, int n_seqs, int group, std:
   while (s0 < n_seqs) {
     int s1 = s0 + 1;
     if (seqs[s0].a_len > 0)
-      while (s1 < n_seqs && seqs[s1].a_len == seqs[s0].a_len && seqs[s1].a_start == seqs[s0].a_start &&
+      while (s1 < n_seqs && seqs[s1].unit == seqs[s0].unit && seqs[s1].a_len == seqs[s0].a_len && seqs[s1].a_start == seqs[s0].a_start &&
              seqs[s1].q_start == seqs[s1 - 1].q_start + seqs[s1 - 1].q_len &&
              seqs[s1].b_start - seqs[s1].q_start == seqs[s0].b_start - seqs[s0].q_start)
         ++s1;

@@ -86,14 +86,17 @@ struct Run {
   std::vector<AttnSeq> seqs;
   bool any_invalid = false;
   bool any_slot = false;  // some token's K/V row differs from its run index (prefix runs behind replicated root rows)
+  int unit = 0;           // tag for the sequences begun from now on (AttnSeq::unit)
   int T() const { return static_cast<int>(tok_src.size()); }
   void clear() {
-    tok_src.clear(); tok_pos.clear(); tok_slot.clear(); key_valid.clear(); seqs.clear(); any_invalid = false; any_slot = false;
+    tok_src.clear(); tok_pos.clear(); tok_slot.clear(); key_valid.clear(); seqs.clear(); any_invalid = false; any_slot = false; unit = 0;
   }
   // returns index of the first token; b_start = K/V row of the sequence's first token (-1: its run index)
   int begin_seq(int a_start, int a_len, int b_start = -1) {
     AttnSeq s;
     s.q_start = T(); s.q_len = 0; s.a_start = a_start; s.a_len = a_len; s.b_start = b_start < 0 ? T() : b_start;
+    static const bool per_seq = getenv("BLIM_ATTN_PERSEQ") != nullptr;   // A/B: never stack two sequences in one tile
+    s.unit = per_seq ? static_cast<int>(seqs.size()) : unit;
     if (s.b_start != s.q_start) any_slot = true;
     seqs.push_back(s);
     return s.q_start;
@@ -967,6 +970,7 @@ static int score_vtg(blim_engine* e, bool prior, const std::vector<std::pair<int
     }
     run.clear();
     for (size_t b = 0; b < batch.size(); ++b) {
+      run.unit = static_cast<int>(b);
       const PromptGroup& g = tt.groups[unit_key[batch[b].unit].second];
       int pos = 0;
       if (R > 0) {
@@ -993,6 +997,7 @@ static int score_vtg(blim_engine* e, bool prior, const std::vector<std::pair<int
     std::vector<int> row_idx, targets, row_off, item_keys;
     row_off.push_back(0);
     for (size_t b = 0; b < batch.size(); ++b) {
+      run.unit = static_cast<int>(b);
       const UnitPlan& up = units[batch[b].unit];
       const PromptGroup& g = tt.groups[unit_key[batch[b].unit].second];
       const int pos0 = static_cast<int>(g.pre.size() + g.post.size()) + n_vis;
@@ -1001,6 +1006,7 @@ static int score_vtg(blim_engine* e, bool prior, const std::vector<std::pair<int
         const int t = keys[it.key].second;
         const int64_t base = tt.off[t];
         const int fl = tt.first_lab[t];
+        if (prior) run.unit = (1 << 24) + ii;   // prior: every text is its own tile group (the one unit holds all texts)
         const int q0 = run.begin_seq(unit_start[b], unit_len[b]);
         for (int j = 0; j < it.suf_len; ++j) run.push(tt.ids[base + fl + j], pos0 + j);
         run.end_seq();
@@ -1125,6 +1131,7 @@ static int score_tvg(blim_engine* e, bool prior, const std::vector<std::pair<int
     run.clear();
     bool any_prefix = false;
     for (size_t b = 0; b < batch.size(); ++b) {
+      run.unit = static_cast<int>(b);
       const int t = unit_text[batch[b].unit];
       const int plen = unit_plen[batch[b].unit];
       if (R > 0) {
@@ -1148,6 +1155,7 @@ static int score_tvg(blim_engine* e, bool prior, const std::vector<std::pair<int
     run.clear();
     std::vector<int> item_keys, item_q0, item_unit_b, item_row0;
     for (size_t b = 0; b < batch.size(); ++b) {
+      run.unit = static_cast<int>(b);
       const UnitPlan& up = units[batch[b].unit];
       // TVG prior: the state of the last text token (position T0-1, CPN-masked as a key) only depends on the visible
       // header, T0 and the token id, not on the video: one 1-token sequence per distinct (T0, token) of this unit
@@ -1159,6 +1167,7 @@ static int score_tvg(blim_engine* e, bool prior, const std::vector<std::pair<int
           if ((T0 - 1) < e->tvg_prefix_len) continue;  // visible as a key: stays inside the item's own sequence
           const std::pair<int, int> k(T0, tt.ids[tt.off[t] + T0 - 1]);
           if (lt_tok.count(k)) continue;
+          run.unit = -1 - static_cast<int>(lt_tok.size());   // its own tile
           lt_tok[k] = run.begin_seq(unit_start[b], unit_len[b]);
           run.push(k.second, T0 - 1, false);
           run.end_seq();
@@ -1168,6 +1177,7 @@ static int score_tvg(blim_engine* e, bool prior, const std::vector<std::pair<int
         const Item& it = items[up.items[ii]];
         const int v = keys[it.key].first, t = keys[it.key].second;
         const int T0 = tt.img_pos[t];
+        run.unit = prior ? (1 << 24) + v : static_cast<int>(b);   // prior: tiles stack the sequences of one video only
         int q0 = run.begin_seq(unit_start[b], unit_len[b]);
         int row0 = -1;
         if (prior) {
@@ -1270,7 +1280,9 @@ extern "C" int blim_score_pairs(blim_engine* e, int kind, const int32_t* pair_v,
     if (kind == BLIM_VTG_PRIOR) return static_cast<uint32_t>(t);
     const uint64_t T0 = static_cast<uint64_t>(tt.img_pos[t]) & 0x3FFF;              // < 2^14: positions are bounded by the rotary table
     const uint64_t tok = static_cast<uint64_t>(tt.ids[tt.off[t] + tt.img_pos[t] - 1]);  // < 2^20 checked below
-    return (static_cast<uint64_t>(hdr_group[t]) << 54) | (T0 << 40) | (tok << 20) | static_cast<uint64_t>(v);
+    // video outermost inside a header group: a video's keys are consecutive in the run, so its attention tiles only stack
+    // its own sequences and its scores do not depend on which other videos are scored alongside (multi-GPU sharding)
+    return (static_cast<uint64_t>(hdr_group[t]) << 54) | (static_cast<uint64_t>(v) << 34) | (T0 << 20) | tok;
   };
   if (kind == BLIM_TVG_PRIOR && (e->V > (1 << 20) || e->n_videos > (1 << 20) || e->rope_n > (1 << 14))) return e->fail("TVG prior key does not fit 64 bits");
   std::vector<std::pair<uint64_t, int>> tagged(n_pairs);
