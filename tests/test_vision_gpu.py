@@ -175,3 +175,28 @@ def test_vit_l_448_clip_vs_fp32_oracle_on_gpu():
         assert _same_rows(feats.cpu().numpy(), want_m.cpu().numpy(), 5e-5)
     finally:
         enc.close()
+
+
+def test_errors_are_reported_not_fatal():
+    """Wrong shapes / unknown names / missing weights come back as VisionError with the engine's message; the extractor stays usable."""
+    case = CASES["tiny_96"]
+    cfg = case["cfg"]
+    enc = V.VisionEncoder(cfg, state_dict=None, device=0, max_clips=2)
+    try:
+        frames = make_frames(case)
+        with pytest.raises(V.VisionError, match="not loaded"):
+            enc.encode(frames)
+        with pytest.raises(V.VisionError, match="shape mismatch"):
+            enc.load_state_dict({"encoder.blocks.0.attn.qkv.weight": torch.zeros(5, 5)})
+        with pytest.raises(V.VisionError, match="unknown parameter"):
+            enc.load_state_dict({"encoder.blocks.0.attn.nonsense": torch.zeros(1)})
+        enc.load_state_dict({"model.vision_tower.vision_tower." + k: v for k, v in V.init_weights(cfg, seed=case["wseed"]).items()})   # prefixed names
+        enc.load_state_dict({"encoder.blocks.9.norm1.weight": torch.ones(cfg.hidden_size)})   # a block behind the select layer: ignored
+        got = enc.encode(frames).cpu().numpy()
+        with torch.no_grad():
+            want = VO.vit_encode(make_weights(case), cfg, frames).numpy()
+        assert np.abs(got - want).max() <= 6e-2
+        with pytest.raises(V.VisionError):
+            enc.merge_tokens(torch.zeros(1, 64, cfg.hidden_size), 64)     # p must exceed the target (mm_projector_builder.py:110)
+    finally:
+        enc.close()
