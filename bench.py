@@ -214,13 +214,13 @@ class Loader:
 # ------------------------------------------------------------------------------------------------ CPU (reference) arm
 def cpu_sample(cfg, weights_cpu, corpus, budget_s=25.0):
     """Times the oracle (CPU restatement of the reference's per-pair algorithm, all host threads) on a bounded sample:
-    three single-pair forwards + criteria per score-matrix kind (v2t: VTG, VTG-CPN, TVG; t2v: VTG, TVG, TVG-CPN), about
+    six single-pair forwards + criteria per score-matrix kind (v2t: VTG, VTG-CPN, TVG; t2v: VTG, TVG, TVG-CPN), about
     10 s of host work on the GPU box's 16 cores.
     Returns (pairs/s, description)."""
     from oracle import blim_oracle as O
     torch.set_num_threads(os.cpu_count())
     vocab = corpus.video_vocab.cpu()
-    n_rep = min(3, len(corpus.vtg_ids) - 1)   # pairs timed per kind: about 10 s of host work per sample on 16 cores
+    n_rep = min(6, len(corpus.vtg_ids) - 1)   # pairs timed per kind: about 10 s of host work per sample on 16 cores
 
     def one(ft, cpn):
         ids_l, lab_l = (corpus.tvg_ids, corpus.tvg_labels) if ft == "tvg" else (corpus.vtg_ids, corpus.vtg_labels)
