@@ -718,15 +718,15 @@ attention_tc2p_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_co
   }
   n_a = (w.a_len + kTcKeys - 1) / kTcKeys;
   n_chunks = n_a + (w.tok0 + w.n_tok - w.kb0 + kTcKeys - 1) / kTcKeys;
+  if (warp == 0) {   // the K / V stages are free (warp 0 itself waited for the previous item's last S and P V): their TMA
+    stage_k(0);      // latency overlaps the Q rows that are still in flight
+    stage_v(0);
+    if (n_chunks > 1) stage_v(1);
+  }
   cp_async_wait<0>();
   fence_proxy_async();
   __syncthreads();   // Q staged; every thread is done with the previous item (its O rows are read, its exchange slots are free)
-  if (warp == 0) {
-    stage_k(0);
-    stage_v(0);
-    if (n_chunks > 1) stage_v(1);
-    issue_s(0, tmem);
-  }
+  if (warp == 0) issue_s(0, tmem);
   float m_ref = -INFINITY, l_part = 0.f;
 
   for (int c = 0; c < n_chunks; ++c) {
