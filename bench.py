@@ -16,7 +16,6 @@ one NCCL all-gather of compact scores per score kind.
 import argparse
 import contextlib
 import json
-import math
 import os
 import subprocess
 import sys

@@ -16,7 +16,6 @@ prompt part set to -100, masks = ids != pad.  The chat template is the reference
 import copy
 import glob
 import json
-import os
 
 import torch
 

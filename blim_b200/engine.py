@@ -1,6 +1,5 @@
 """Python handle on the C-ABI engine.  PyTorch is used only for device memory, streams and dtype bookkeeping."""
 import ctypes
-import math
 from dataclasses import dataclass
 
 import numpy as np

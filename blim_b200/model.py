@@ -10,7 +10,7 @@ from types import SimpleNamespace
 
 import torch
 
-from .engine import Engine, ModelConfig, TEXTS_TVG, TEXTS_VTG
+from .engine import Engine, ModelConfig
 
 IGNORE_INDEX = -100
 IMAGE_TOKEN_INDEX = -200
