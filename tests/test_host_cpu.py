@@ -134,6 +134,25 @@ def test_extractor_fails_loudly_without_gpu_and_chunks_cover_the_list():
     assert len(V.param_shapes(cfg)) == 2 + 13 * 23 + 2
 
 
+def test_committed_ncu_launch_list_reproduces_the_share_summary(tmp_path):
+    """profiles/: the per-kernel shares the docs quote are what tools/ncu_summary.py derives from the committed launch list."""
+    import glob
+    import json
+    import subprocess
+    import sys
+    lists = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_ncu_launches_c2_n96_v1?.csv")))
+    assert lists, "no committed ncu launch list"
+    out = str(tmp_path / "shares.json")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), "shares", out, lists[-1]], check=True)
+    got = json.load(open(out))
+    tag = lists[-1].rsplit("_", 1)[1].split(".")[0]
+    want = json.load(open(os.path.join(ROOT, "profiles", f"r01_ncu_launch_shares_{tag}.json")))
+    assert [k["kernel"] for k in got["kernels"][:6]] == [k["kernel"] for k in want["kernels"][:6]]
+    assert abs(got["total_ms"] - want["total_ms"]) < 1e-6
+    gemm = sum(k["share_pct"] for k in got["kernels"] if k["kernel"].startswith("gemm_tcgen05_kernel"))
+    assert 85.0 < gemm < 97.0          # the dominant kernel family of the step (bench roofline: tcgen05 GEMMs)
+
+
 def test_balanced_owner_ranks_lpt():
     """Multi-GPU sharding: every owner on exactly one rank, loads within one largest item of each other, deterministic."""
     from blim_b200.retrieval import balanced_owner_ranks
