@@ -101,9 +101,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    if not os.environ.get("BLIM_LIB"):
+        # never load a binary built from other sources: build() compares a digest of csrc/ + include/ + flags with the
+        # stamp next to the .so and returns at once when it is fresh (the .so and its stamp travel to the GPU box together)
         from . import build as _build
-        _build.build()
+        try:
+            _build.build()
+        except Exception as ex:
+            if not _build.is_fresh():
+                raise ImportError(f"{LIB_PATH} is missing or stale and could not be rebuilt ({ex}); there is no CPU fallback") from ex
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing: build it with `python -m blim_b200.build` (no CPU fallback exists)")
     lib = ctypes.CDLL(LIB_PATH)

@@ -49,6 +49,14 @@ def _digest():
     return h.hexdigest()
 
 
+def is_fresh():
+    """True when the shared object next to the sources was built from exactly these sources and flags."""
+    if not (os.path.exists(LIB) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as fh:
+        return fh.read().strip() == _digest()
+
+
 def build(force=False, verbose=False):
     """Compile the engine if the sources changed.  Returns the path of the shared object."""
     digest = _digest()

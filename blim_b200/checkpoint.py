@@ -26,11 +26,28 @@ def _plain_name(name):
     return name
 
 
-def merge_lora(base_state_dict, trainable_state_dict, lora_r, lora_alpha, dtype=torch.bfloat16):
+_MLP = "model.mm_projector.mlp."
+_TVG_MLP = "model.mm_projector.tvg_mlp."
+
+
+def seed_tvg_mlp(state_dict):
+    """The reference builds tvg_mlp as `copy.deepcopy(mm_projector.mlp)` AFTER the PEFT wrap (main.py:100-101): its frozen
+    base weights and biases are the base mlp's, whatever the constructor's random tvg_mlp was
+    (mm_projector_builder.py:91-93), and they are never saved (util/misc.py:282-285 stores requires_grad tensors only).
+    Overwrites model.mm_projector.tvg_mlp.{0,2}.{weight,bias} with the mlp tensors, in place; returns the dict."""
+    for key in [k for k in state_dict if k.startswith(_MLP)]:
+        state_dict[_TVG_MLP + key[len(_MLP):]] = state_dict[key]
+    return state_dict
+
+
+def merge_lora(base_state_dict, trainable_state_dict, lora_r, lora_alpha, dtype=torch.bfloat16, tvg_from_mlp=True):
     """Returns a new state dict: base weights with every LoRA pair merged (W + alpha/r * B @ A) and every other tensor of
-    the checkpoint (visual_head.weight, ...) overriding the base tensor of the same plain name."""
+    the checkpoint (visual_head.weight, ...) overriding the base tensor of the same plain name.  `tvg_from_mlp`: the
+    tvg_mlp adapters sit on a copy of the base mlp (see seed_tvg_mlp), not on whatever tvg_mlp the base dict carries."""
     scale = float(lora_alpha) / float(lora_r)
     out = {_plain_name(k): v for k, v in base_state_dict.items()}
+    if tvg_from_mlp:
+        seed_tvg_mlp(out)
     pending = dict(trainable_state_dict)
     merged = []
     for key in list(pending):
@@ -61,7 +78,9 @@ def merge_lora(base_state_dict, trainable_state_dict, lora_r, lora_alpha, dtype=
 def load_finetuned(model, base_state_dict, checkpoint, lora_r, lora_alpha):
     """model: blim_b200.model.BlimModel.  checkpoint: the reference's `{'model': trainable tensors, ...}` dict or a path."""
     if isinstance(checkpoint, str):
-        checkpoint = torch.load(checkpoint, map_location="cpu")
+        # reference checkpoints also hold the optimizer / scaler state and an argparse.Namespace (util/misc.py:288-294):
+        # a trusted local file, so the full unpickler is what the reference itself uses (main.py:126)
+        checkpoint = torch.load(checkpoint, map_location="cpu", weights_only=False)
     trainable = checkpoint["model"] if "model" in checkpoint else checkpoint
     sd, merged = merge_lora(base_state_dict, trainable, lora_r, lora_alpha)
     ignored = model.load_state_dict(sd)

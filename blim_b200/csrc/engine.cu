@@ -58,8 +58,17 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// sub-tensors of a layer that blim_load_weight has filled (the fused buffers are allocated by the first of them)
+enum : unsigned {
+  kLdQ = 1u << 0, kLdK = 1u << 1, kLdV = 1u << 2, kLdQb = 1u << 3, kLdKb = 1u << 4, kLdVb = 1u << 5, kLdO = 1u << 6, kLdGate = 1u << 7,
+  kLdUp = 1u << 8, kLdDown = 1u << 9, kLdLn1 = 1u << 10, kLdLn2 = 1u << 11, kLdAll = (1u << 12) - 1
+};
+static const char* const kLdNames[12] = {"self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight", "self_attn.q_proj.bias",
+                                         "self_attn.k_proj.bias", "self_attn.v_proj.bias", "self_attn.o_proj.weight", "mlp.gate_proj.weight",
+                                         "mlp.up_proj.weight", "mlp.down_proj.weight", "input_layernorm.weight", "post_attention_layernorm.weight"};
 struct LayerW {
   DevBuf w_qkv, w_o, w_gu, w_down, b_qkv, ln1, ln2;
+  unsigned loaded = 0;  // kLd* bits
   bool folded = false;  // input_layernorm / post_attention_layernorm weights folded into w_qkv / w_gu (fused RMSNorm)
 };
 struct ProjW {
@@ -154,6 +163,7 @@ struct blim_engine {
   size_t arena_cap = 0, arena_off = 0;
   bool arena_disabled = false;
   bool root_share = true;   // shared prompt-header root for the prefixes (BLIM_ROOT=0 disables)
+  bool attr_fuse = false, attr_topk = false;   // cudaFuncSetAttribute done on this engine's device
   bool fuse_norm = false;  // BLIM_FUSE_NORM=1: RMSNorm fused into the GEMMs around it (measured slower than the standalone kernel)
   DevBuf ssq, rstd;
   CUtensorMap tm_kp, tm_vp, tm_kown, tm_vown;  // K / V buffers as TMA tensors (tcgen05 attention)
@@ -290,6 +300,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
   e->Pmax = cfg->max_prefix_tokens > 0 ? cfg->max_prefix_tokens : 32768;
   e->Umax = std::min(e->Pmax, 8192);
   e->gemm.num_sms = prop.multiProcessorCount;
+  e->gemm.device = device;
   {
     const char* a = getenv("BLIM_ATTN");
     e->attn_tc = !(a && std::string(a) == "mma");
@@ -421,18 +432,18 @@ extern "C" int blim_load_weight(blim_engine* e, const char* name_c, const void* 
                      rest.find("v_proj.weight") != std::string::npos || rest.find("gate_proj") != std::string::npos ||
                      rest.find("up_proj") != std::string::npos || rest.find("layernorm") != std::string::npos))
       return e->fail("layer " + std::to_string(li) + " is already finalised (norm weights folded into its GEMM weights): create a new engine to reload " + name);
-    if (rest == "self_attn.q_proj.weight") { if (!is2(NQ, H)) return shape_err(); return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NQ, H, 0, 0, 0, st); }
-    if (rest == "self_attn.k_proj.weight") { if (!is2(NKVD, H)) return shape_err(); return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NKVD, H, NQ, 0, 0, st); }
-    if (rest == "self_attn.v_proj.weight") { if (!is2(NKVD, H)) return shape_err(); return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NKVD, H, NQ + NKVD, 0, 0, st); }
-    if (rest == "self_attn.q_proj.bias") { if (!is1(NQ)) return shape_err(); return repack_f32(e, w.b_qkv, NQKV, 0, src, dtype, NQ, 1, st); }
-    if (rest == "self_attn.k_proj.bias") { if (!is1(NKVD)) return shape_err(); return repack_f32(e, w.b_qkv, NQKV, NQ, src, dtype, NKVD, 1, st); }
-    if (rest == "self_attn.v_proj.bias") { if (!is1(NKVD)) return shape_err(); return repack_f32(e, w.b_qkv, NQKV, NQ + NKVD, src, dtype, NKVD, 1, st); }
-    if (rest == "self_attn.o_proj.weight") { if (!is2(H, NQ)) return shape_err(); return repack_bf16(e, w.w_o, H, src, dtype, H, NQ, 0, 0, 0, st); }
-    if (rest == "mlp.gate_proj.weight") { if (!is2(I, H)) return shape_err(); return repack_bf16(e, w.w_gu, 2 * static_cast<size_t>(I), src, dtype, I, H, 0, 128, 0, st); }
-    if (rest == "mlp.up_proj.weight") { if (!is2(I, H)) return shape_err(); return repack_bf16(e, w.w_gu, 2 * static_cast<size_t>(I), src, dtype, I, H, 0, 128, 1, st); }
-    if (rest == "mlp.down_proj.weight") { if (!is2(H, I)) return shape_err(); return repack_bf16(e, w.w_down, H, src, dtype, H, I, 0, 0, 0, st); }
-    if (rest == "input_layernorm.weight") { if (!is1(H)) return shape_err(); return repack_f32(e, w.ln1, H, 0, src, dtype, H, 1, st); }
-    if (rest == "post_attention_layernorm.weight") { if (!is1(H)) return shape_err(); return repack_f32(e, w.ln2, H, 0, src, dtype, H, 1, st); }
+    if (rest == "self_attn.q_proj.weight") { if (!is2(NQ, H)) return shape_err(); w.loaded |= kLdQ; return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NQ, H, 0, 0, 0, st); }
+    if (rest == "self_attn.k_proj.weight") { if (!is2(NKVD, H)) return shape_err(); w.loaded |= kLdK; return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NKVD, H, NQ, 0, 0, st); }
+    if (rest == "self_attn.v_proj.weight") { if (!is2(NKVD, H)) return shape_err(); w.loaded |= kLdV; return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NKVD, H, NQ + NKVD, 0, 0, st); }
+    if (rest == "self_attn.q_proj.bias") { if (!is1(NQ)) return shape_err(); w.loaded |= kLdQb; return repack_f32(e, w.b_qkv, NQKV, 0, src, dtype, NQ, 1, st); }
+    if (rest == "self_attn.k_proj.bias") { if (!is1(NKVD)) return shape_err(); w.loaded |= kLdKb; return repack_f32(e, w.b_qkv, NQKV, NQ, src, dtype, NKVD, 1, st); }
+    if (rest == "self_attn.v_proj.bias") { if (!is1(NKVD)) return shape_err(); w.loaded |= kLdVb; return repack_f32(e, w.b_qkv, NQKV, NQ + NKVD, src, dtype, NKVD, 1, st); }
+    if (rest == "self_attn.o_proj.weight") { if (!is2(H, NQ)) return shape_err(); w.loaded |= kLdO; return repack_bf16(e, w.w_o, H, src, dtype, H, NQ, 0, 0, 0, st); }
+    if (rest == "mlp.gate_proj.weight") { if (!is2(I, H)) return shape_err(); w.loaded |= kLdGate; return repack_bf16(e, w.w_gu, 2 * static_cast<size_t>(I), src, dtype, I, H, 0, 128, 0, st); }
+    if (rest == "mlp.up_proj.weight") { if (!is2(I, H)) return shape_err(); w.loaded |= kLdUp; return repack_bf16(e, w.w_gu, 2 * static_cast<size_t>(I), src, dtype, I, H, 0, 128, 1, st); }
+    if (rest == "mlp.down_proj.weight") { if (!is2(H, I)) return shape_err(); w.loaded |= kLdDown; return repack_bf16(e, w.w_down, H, src, dtype, H, I, 0, 0, 0, st); }
+    if (rest == "input_layernorm.weight") { if (!is1(H)) return shape_err(); w.loaded |= kLdLn1; return repack_f32(e, w.ln1, H, 0, src, dtype, H, 1, st); }
+    if (rest == "post_attention_layernorm.weight") { if (!is1(H)) return shape_err(); w.loaded |= kLdLn2; return repack_f32(e, w.ln2, H, 0, src, dtype, H, 1, st); }
   }
   e->weights_loaded--;
   return 2;  // not a parameter of the scoring path (vision tower, rotary buffers, ...): ignored
@@ -564,23 +575,26 @@ extern "C" int blim_set_tvg_prefix_length(blim_engine* e, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------ building blocks
-static int check_ready(blim_engine* e) {
+static int check_ready(blim_engine* e, cudaStream_t st) {
   if (!e->embed.p || !e->lm_head.p || !e->norm.p) return e->fail("weights not loaded (embed_tokens / lm_head / norm)");
   for (int l = 0; l < e->NL; ++l) {
     const LayerW& w = e->layers[l];
-    if (!w.w_qkv.p || !w.w_o.p || !w.w_gu.p || !w.w_down.p || !w.b_qkv.p || !w.ln1.p || !w.ln2.p)
-      return e->fail("weights of layer " + std::to_string(l) + " not loaded");
+    if (w.loaded != kLdAll) {   // the fused QKV / gate|up buffers exist as soon as ONE of their parts is loaded: check every part
+      std::string missing;
+      for (int b = 0; b < 12; ++b)
+        if (!(w.loaded & (1u << b))) missing += std::string(missing.empty() ? "" : ", ") + kLdNames[b];
+      return e->fail("weights of layer " + std::to_string(l) + " not loaded: " + missing);
+    }
   }
   if (!e->rope_cos.p) return e->fail("rotary table not set (blim_set_rope)");
   if (e->fuse_norm) {
     for (int l = 0; l < e->NL; ++l) {
       LayerW& w = e->layers[l];
       if (w.folded) continue;
-      fold_norm_weight_kernel<<<2048, 256>>>(w.w_qkv.as<bf16>(), w.ln1.as<float>(), static_cast<size_t>(e->NQKV), e->H);
-      fold_norm_weight_kernel<<<2048, 256>>>(w.w_gu.as<bf16>(), w.ln2.as<float>(), 2 * static_cast<size_t>(e->I), e->H);
+      fold_norm_weight_kernel<<<2048, 256, 0, st>>>(w.w_qkv.as<bf16>(), w.ln1.as<float>(), static_cast<size_t>(e->NQKV), e->H);
+      fold_norm_weight_kernel<<<2048, 256, 0, st>>>(w.w_gu.as<bf16>(), w.ln2.as<float>(), 2 * static_cast<size_t>(e->I), e->H);
       w.folded = true;
     }
-    CKE(cudaDeviceSynchronize());  // one-time (legacy-stream launches above): everything later is stream-ordered
   }
   return 0;
 }
@@ -1250,8 +1264,8 @@ extern "C" int blim_score_pairs(blim_engine* e, int kind, const int32_t* pair_v,
   if (!pair_v || !pair_t || !out_dev || n_pairs < 0 || n_pairs > (1ll << 30)) return e->fail("bad pair arguments");
   if (kind < 0 || kind > 3) return e->fail("bad score kind");
   CKE(cudaSetDevice(e->device));
-  CKR(check_ready(e));
   cudaStream_t st = S(stream);
+  CKR(check_ready(e, st));
   const bool is_tvg = kind == BLIM_TVG || kind == BLIM_TVG_PRIOR;
   const bool prior = kind == BLIM_VTG_PRIOR || kind == BLIM_TVG_PRIOR;
   const TextTable& tt = e->texts[is_tvg ? BLIM_TEXTS_TVG : BLIM_TEXTS_VTG];
@@ -1314,8 +1328,8 @@ extern "C" int blim_forward_logits(blim_engine* e, const void* embeds, const int
   if (!e) return 1;
   if (!embeds || B <= 0 || L <= 0) return e->fail("bad forward arguments");
   CKE(cudaSetDevice(e->device));
-  CKR(check_ready(e));
   cudaStream_t st = S(stream);
+  CKR(check_ready(e, st));
   if (L > e->Tmax) return e->fail("sequence longer than max_run_tokens");
   const int seq_per_run = std::max(1, e->Tmax / L);
   std::vector<int32_t> mask_h;
@@ -1407,10 +1421,9 @@ extern "C" int blim_fuse_rerank(blim_engine* e, const blim_fuse_cfg* c, const in
   f.cpn_zero_f64 = c->cpn_zero_f64;
   const size_t smem = static_cast<size_t>(k) * (sizeof(double) + sizeof(int)) + n_cols;
   if (smem > 200 * 1024) return e->fail("fuse_rerank: row too wide for shared memory");
-  static bool attr = false;
-  if (!attr) {
+  if (!e->attr_fuse) {   // per engine = per device (function attributes are per device)
     CKE(cudaFuncSetAttribute(fuse_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
+    e->attr_fuse = true;
   }
   fuse_rerank_kernel<<<n_rows, 256, smem, S(stream)>>>(f, cand_idx, cand, prior, query, iv2, n_rows, n_cols, k, row0, fused_out, order_out,
                                                         gt_rank_out, zero_count);
@@ -1437,10 +1450,9 @@ extern "C" int blim_topk_rows(blim_engine* e, const float* mat, int n_rows, int 
   const int warps = 4;
   const size_t smem = static_cast<size_t>(warps) * (n_cols * sizeof(float) + ((n_cols + 31) / 32) * sizeof(unsigned));
   if (smem > 200 * 1024) return e->fail("topk: row too wide for shared memory");
-  static bool attr = false;
-  if (!attr) {
+  if (!e->attr_topk) {
     CKE(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
+    e->attr_topk = true;
   }
   topk_rows_kernel<<<(n_rows + warps - 1) / warps, warps * 32, smem, S(stream)>>>(mat, n_rows, n_cols, k, idx_out, val_out);
   CKL();

@@ -673,6 +673,7 @@ struct GemmLaunchCtx {
   bool sb_auto = true;  // per-shape choice between the 40 MB slab and one m-tile at a time; BLIM_GEMM_SB_MB / _MIN switch it off
   int cta_group = 1;  // 1: one CTA per tile, 2: CTA pairs (cta_group::2, 256-row tiles)
   long long launches = 0;
+  int device = 0;     // CUDA device of the owning engine
 };
 
 template <class Epi, int kCtaGroup>
@@ -708,11 +709,12 @@ inline cudaError_t launch_gemm_impl(GemmLaunchCtx& ctx, const __nv_bfloat16* A, 
   d.sb_tiles = static_cast<int>(sb);
   d.l2_hints = ctx.l2_hints;
   auto kern = gemm_tcgen05_kernel<Epi, kCtaGroup>;
-  static bool attr_set = false;  // one static per instantiation
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per instantiation AND per device (function attributes are per device)
+  const int dev_slot = ctx.device & 63;
+  if (!attr_set[dev_slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev_slot] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(workers * kCtaGroup));

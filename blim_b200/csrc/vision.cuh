@@ -452,6 +452,7 @@ extern "C" int blim_vision_create(const blim_vision_cfg* cfg, int device, blim_v
   v->max_clips = cfg->max_clips > 0 ? cfg->max_clips : 16;
   if (v->TL <= cfg->tome_tokens_per_frame * v->FPC) { delete v; return bad("a clip must have more tokens than the merging target (mm_projector_builder.py:110)"); }
   v->gemm.num_sms = prop.multiProcessorCount;
+  v->gemm.device = device;
   v->gemm.cta_group = 2;
   v->attn_version = dh == 64 ? 4 : 2;   // v4 (issue warp, two P tiles) wins at head_dim 64; at 128 its 96-register budget spills
   if (const char* a = getenv("BLIM_VIS_ATTN")) v->attn_version = (atoi(a) >= 2 && atoi(a) <= 4) ? atoi(a) : v->attn_version;

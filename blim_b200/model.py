@@ -112,8 +112,19 @@ class BlimModel:
         return None, None, mask, past_key_values, embeds, new_labels
 
     # ------------------------------------------------------------------ corpus registration for the fast path
+    # The caches below avoid re-uploading a corpus for each of the six compute_*_scores_x calls of one evaluation.  They
+    # are keyed on the CONTENT location (storage pointers of the first / last tensor, shapes, in-place version counters),
+    # not on id(): a new list of the same length can reuse the id of a garbage-collected one.
+    @staticmethod
+    def _tensors_key(x):
+        if torch.is_tensor(x):
+            return ("t", x.data_ptr(), tuple(x.shape), str(x.dtype), x._version)
+        x = list(x)
+        ends = [t for t in (x[0], x[-1])] if x else []
+        return ("l", len(x)) + tuple((t.data_ptr(), tuple(t.shape), str(t.dtype), t._version) if torch.is_tensor(t) else id(t) for t in ends)
+
     def ensure_videos(self, video):
-        key = ("video", id(video), len(video))
+        key = ("video", self._tensors_key(video))
         if self._corpus_keys.get("video") != key:
             if torch.is_tensor(video):
                 feats = video
@@ -128,7 +139,7 @@ class BlimModel:
             self._corpus_keys.pop("vocab", None)
 
     def ensure_texts(self, which, input_ids, attention_masks, labels):
-        key = (which, id(input_ids), id(labels), tuple(input_ids.shape) if torch.is_tensor(input_ids) else len(input_ids))
+        key = (which, self._tensors_key(input_ids), self._tensors_key(labels), self._tensors_key(attention_masks) if attention_masks is not None else None)
         if self._corpus_keys.get(("texts", which)) != key:
             if torch.is_tensor(input_ids):   # padded [N, Lmax] + masks (padding_ids output, retrieval_utils.py:155-167)
                 m = attention_masks.bool().cpu()
@@ -140,7 +151,7 @@ class BlimModel:
             self._corpus_keys[("texts", which)] = key
 
     def ensure_vocab(self, video_vocab, tvg_video_labels):
-        key = ("vocab", id(video_vocab), id(tvg_video_labels))
+        key = ("vocab", self._tensors_key(video_vocab), self._tensors_key(torch.as_tensor(tvg_video_labels)))
         if self._corpus_keys.get("vocab") != key:
             self.engine.set_video_vocab(video_vocab, torch.as_tensor(tvg_video_labels).cpu().numpy())
             self._corpus_keys["vocab"] = key

@@ -247,6 +247,7 @@ def evaluation(model, data_loader, device, tokenizer, args):
     `args.iv2_scores = {"v2t": ..., "t2v": ...}` when present (synthetic runs)."""
     m = _engine_model(model)
     eng = m.engine
+    m._corpus_keys.clear()   # one upload per evaluation() call: this call's loader output is what gets scored
     start_time = time.time()
     video, tvg_video_labels = [], []
     vtg_ids, vtg_labels, vtg_masks = [], [], []

@@ -1,8 +1,10 @@
-"""TEST INFRASTRUCTURE -- imports the UNMODIFIED reference (mlvlab/BLiM) from /root/reference to pin the oracle.
+"""TEST INFRASTRUCTURE -- imports the UNMODIFIED reference (mlvlab/BLiM) to pin the oracle and to serve as comparator.
 
-Only usable in the build container (the GPU box has no /root/reference); nothing in the product imports this.
-It is used by oracle/make_golden.py to generate the fixtures under tests/golden/ and by the (CPU) tests that compare
-oracle/blim_oracle.py with the real reference when the reference tree is present.
+Where the reference comes from, in this order: $BLIM_REF, /root/reference (build container only), baseline/_ref/ (a
+git-ignored verbatim copy of the reference's .py files that __graft_entry__.build() makes in the build container; it
+travels to the GPU box with the repo snapshot, never enters the history).  Nothing in the product imports this module.
+Users: oracle/make_golden.py (fixtures under tests/golden/), the tests that compare oracle/blim_oracle.py and the CUDA
+engine with the real reference, tools/parity_7b.py and bench.py's reference arm / rank-parity check.
 
 Shims: stub modules for packages the vision tower / video IO import but the scoring path never
 calls (timm.layers, av, imageio, decord), and three transformers-5 workarounds on the config object.
@@ -13,11 +15,42 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("BLIM_REF", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIPPED = os.path.join(_REPO, "baseline", "_ref")
+
+
+def _find_root():
+    for cand in (os.environ.get("BLIM_REF"), "/root/reference", SHIPPED):
+        if cand and os.path.isfile(os.path.join(cand, "retrieval_utils.py")) and os.path.isdir(os.path.join(cand, "videochat_flash")):
+            return cand
+    return os.environ.get("BLIM_REF", "/root/reference")
+
+
+REF_ROOT = _find_root()
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REF_ROOT, "videochat_flash"))
+    return os.path.isfile(os.path.join(REF_ROOT, "retrieval_utils.py")) and os.path.isdir(os.path.join(REF_ROOT, "videochat_flash"))
+
+
+def ship_reference(src="/root/reference", dst=SHIPPED):
+    """Verbatim copy of the reference's Python sources into the git-ignored baseline/_ref/ so that they reach the GPU box
+    (which has no /root/reference).  Called by __graft_entry__.build() in the build container; returns the file count."""
+    import shutil
+    if not os.path.isdir(os.path.join(src, "videochat_flash")):
+        return 0
+    n = 0
+    for dirpath, dirnames, filenames in os.walk(src):
+        dirnames[:] = [d for d in dirnames if d not in (".git", "asset", "__pycache__")]
+        for f in filenames:
+            if not f.endswith((".py", ".md", ".sh")) and f != "LICENSE":
+                continue
+            rel = os.path.relpath(os.path.join(dirpath, f), src)
+            out = os.path.join(dst, rel)
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            shutil.copyfile(os.path.join(dirpath, f), out)
+            n += 1
+    return n
 
 
 def _install_stubs():
@@ -74,9 +107,10 @@ class _Wrap(torch.nn.Module):
         return self.module(*a, **k)
 
 
-def build_reference_model(cfg, state_dict, dtype=torch.float32, image_token_id=None):
+def build_reference_model(cfg, state_dict, dtype=torch.float32, image_token_id=None, device=None):
     """Instantiate the reference VideoChatFlashQwenForCausalLM for `cfg` (blim_b200.engine.ModelConfig) and load
-    `state_dict` (reference parameter names).  Returns the wrapped model (with .module) and the reference modules."""
+    `state_dict` (reference parameter names).  Returns the wrapped model (with .module) and the reference modules.
+    With `device` the module is constructed directly there in `dtype` (7B: no 30 GB host-side fp32 init)."""
     ru, tu, mvf = import_reference()
     c = mvf.VideoChatFlashQwenConfig(
         hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_layers, num_attention_heads=cfg.num_heads,
@@ -97,7 +131,16 @@ def build_reference_model(cfg, state_dict, dtype=torch.float32, image_token_id=N
     c.use_cache = False
     c._attn_implementation = "sdpa"
     object.__setattr__(c, "rope_theta", cfg.rope_theta)
-    model = mvf.VideoChatFlashQwenForCausalLM(c)
+    if device is None:
+        model = mvf.VideoChatFlashQwenForCausalLM(c)
+    else:
+        old = torch.get_default_dtype()
+        torch.set_default_dtype(dtype)
+        try:
+            with torch.device(device):
+                model = mvf.VideoChatFlashQwenForCausalLM(c)
+        finally:
+            torch.set_default_dtype(old)
     missing, unexpected = model.load_state_dict(state_dict, strict=False)
     need = [k for k in missing if not k.startswith("model.vision_tower") and "rotary_emb" not in k]
     assert not need, f"reference parameters not provided: {need[:5]}"

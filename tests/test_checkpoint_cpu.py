@@ -42,3 +42,33 @@ def test_merge_matches_adapter_forward():
     assert torch.equal(merged["model.norm.weight"], base["model.norm.weight"])
     with pytest.raises(ValueError):
         merge_lora(base, ckpt, 4, alpha)
+
+
+@pytest.mark.parametrize("with_random_tvg_mlp", [False, True])
+def test_reference_checkpoint_layout(tmp_path, with_random_tvg_mlp):
+    """The reference's real key layout (main.py:99-111, util/misc.py:276-297): tvg_mlp adapters sit on a COPY OF THE BASE
+    mlp, whether the base dict has no tvg_mlp at all (HF checkpoint) or an unrelated random one (constructor init)."""
+    from blim_b200.checkpoint import load_finetuned
+    from blim_b200.engine import ModelConfig
+    from tests import ckpt_fixture as F
+    cfg = ModelConfig.tiny()
+    base = F.base_state_dict(cfg, with_random_tvg_mlp=with_random_tvg_mlp)
+    ckpt, deltas = F.make_reference_checkpoint(cfg)
+    path = tmp_path / "checkpoint_best.pth"
+    torch.save(ckpt, path)                                  # holds an argparse.Namespace + optimizer state like the reference's
+
+    class Sink:                                             # stands in for BlimModel (no GPU here)
+        def load_state_dict(self, sd):
+            self.sd = sd
+            return []
+    sink = Sink()
+    merged_names, _ = load_finetuned(sink, base, str(path), 8, 32)
+    want = F.expected_merged(cfg, base, ckpt, deltas)
+    assert len(merged_names) == len(F.adapted_linears(cfg))
+    for k, w in want.items():
+        got = sink.sd[k].float()
+        tol = 0.0 if k == "visual_head.weight" else 2.0 ** -8 * float(w.abs().max())       # one bf16 rounding of the merged weight
+        assert (got - w).abs().max() <= tol, k
+    # the tvg_mlp base really is the mlp base, not the base dict's own tvg_mlp
+    k = "model.mm_projector.tvg_mlp.0.bias"
+    assert torch.equal(sink.sd[k].float(), base["model.mm_projector.mlp.0.bias"].float())
