@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "act_type.cuh"
 #include "attention.cuh"
 #include "gemm_sm100.cuh"
 #include "ptx_sm100.cuh"
@@ -42,8 +43,8 @@ struct AttnWorkTc {
   int pad1, pad2;
 };
 struct AttnParamsTc {
-  const __nv_bfloat16* q;
-  __nv_bfloat16* o;
+  const void* q;              // 16-bit elements in the kernel's operand format T16 (act_type.cuh)
+  void* o;
   int a_row0;                 // row offset of this layer inside the tensor map of the prefix K / V buffers
   int b_row0;                 // row offset inside the tensor map of the own-run K / V buffers
   const uint8_t* key_valid;   // per own token, nullptr = all valid
@@ -58,245 +59,6 @@ struct AttnParamsTc {
 constexpr int kTcKeys = 64;       // keys per chunk
 constexpr int kTcThreads = 128;
 constexpr int kTcTmemCols = 256;  // S (64) + Oc (<= 128), power of two
-
-template <int DH>
-constexpr int attn_tc_smem_bytes() {
-  // Q (DH/64 x 16 KB) + K chunk (DH/64 x 8 KB) + V chunk (DH/64 x 8 KB) + P (16 KB) + alignment slack
-  return (DH / 64) * 16384 + 2 * (DH / 64) * 8192 + 16384 + 1024;
-}
-
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  tmem_ld32(taddr, r);
-  tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-template <int DH>
-__global__ void __launch_bounds__(kTcThreads, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_constant__ CUtensorMap tm_va,
-                    const __grid_constant__ CUtensorMap tm_kb, const __grid_constant__ CUtensorMap tm_vb, const AttnParamsTc p) {
-  constexpr int kSub = DH / 64;  // 64-column sub-tiles along head_dim
-  constexpr uint32_t kChunkBytes = kSub * 8192;
-  extern __shared__ uint8_t smem_raw_tc[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* s_q = smem;                       // kSub x [128 rows x 128 B]
-  uint8_t* s_k = s_q + kSub * 16384;         // kSub x [64 keys x 128 B]   (K-major B of S = Q K^T)
-  uint8_t* s_v = s_k + kSub * 8192;          // kSub x [64 keys x 128 B]   (MN-major B of Oc = P V: sub-tile = 64 head_dim columns)
-  uint8_t* s_p = s_v + kSub * 8192;          // [128 rows x 64 keys]       (K-major A of Oc = P V)
-  __shared__ uint64_t bar_s, bar_o, bar_k, bar_v;
-  __shared__ uint32_t tmem_slot;
-
-  const AttnWorkTc w = p.works[blockIdx.x];
-  const int kvh = blockIdx.y;
-  const int G = p.group;
-  const int tid = threadIdx.x, warp = tid >> 5;
-
-  if (tid == 0) {
-    mbar_init(&bar_s, 1);
-    mbar_init(&bar_o, 1);
-    mbar_init(&bar_k, 1);
-    mbar_init(&bar_v, 1);
-    fence_barrier_init();
-    tma_prefetch_desc(&tm_ka);
-    tma_prefetch_desc(&tm_va);
-    tma_prefetch_desc(&tm_kb);
-    tma_prefetch_desc(&tm_vb);
-  }
-  if (warp == 0) tmem_alloc<1>(&tmem_slot, kTcTmemCols);
-
-  // ---- this thread's row
-  const int tok_local = tid / G, head = tid - tok_local * G;
-  const bool row_ok = tok_local < w.n_tok;
-  const int rt = w.tok0 + (row_ok ? tok_local : 0);        // run token index of the row
-  const int seq_lo = (row_ok && p.tok_seq_start != nullptr) ? __ldg(p.tok_seq_start + rt) : 0;
-  {
-    // Q row -> swizzled K-major tile (zero-filled for padding rows)
-    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.q_stride + (kvh * G + head) * DH;
-#pragma unroll
-    for (int c = 0; c < DH / 8; ++c)
-      cp_async16(s_q + (c >> 3) * 16384 + sw128_offset(tid, (c & 7) * 8), src + c * 8, row_ok ? 16 : 0);
-    cp_async_commit();
-  }
-
-  const int n_a = (w.a_len + kTcKeys - 1) / kTcKeys;
-  const int own_len = w.tok0 + w.n_tok - w.kb0;            // own keys [kb0, tok0 + n_tok)
-  const int n_chunks = n_a + (own_len + kTcKeys - 1) / kTcKeys;
-
-  // chunk c -> key count, first key (segment A: index inside the prefix; own: run token index), tensor-map row
-  auto chunk_keys = [&](int c, int& nk, int& key0, bool& own, int& tm_row) {
-    if (c < n_a) {
-      own = false;
-      key0 = c * kTcKeys;
-      nk = min(kTcKeys, w.a_len - key0);
-      tm_row = p.a_row0 + w.a_start + key0;
-    } else {
-      own = true;
-      key0 = w.kb0 + (c - n_a) * kTcKeys;
-      nk = min(kTcKeys, w.tok0 + w.n_tok - key0);
-      tm_row = p.b_row0 + key0 + w.b_off;
-    }
-  };
-  // one elected thread: TMA a [64 keys x DH] chunk as kSub boxes of 64 columns
-  auto stage = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tm_row) {
-    mbar_arrive_expect_tx(bar, kChunkBytes);
-#pragma unroll
-    for (int sub = 0; sub < kSub; ++sub) tma_load_2d(dst + sub * 8192, tm, bar, kvh * DH + sub * 64, tm_row);
-  };
-
-  tc_fence_before();
-  __syncthreads();   // barriers initialised, TMEM allocated
-  tc_fence_after();
-  if (tid == 0) {
-    int nk, key0, row; bool own;
-    chunk_keys(0, nk, key0, own, row);
-    stage(s_k, own ? &tm_kb : &tm_ka, &bar_k, row);
-    stage(s_v, own ? &tm_vb : &tm_va, &bar_v, row);
-  }
-  const uint32_t tmem = tmem_slot;
-  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);   // this thread's TMEM lane
-  const uint32_t t_s = t_row, t_o = t_row + 64;
-
-  float o[DH];
-#pragma unroll
-  for (int i = 0; i < DH; ++i) o[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;   // running max in scaled (log2) units
-  cp_async_wait<0>();                      // this thread's Q row has landed
-
-  for (int c = 0; c < n_chunks; ++c) {
-    int nk, key0, tm_row_unused; bool own;
-    chunk_keys(c, nk, key0, own, tm_row_unused);
-    const int nk16 = (nk + 15) & ~15;
-    const uint32_t ph = static_cast<uint32_t>(c & 1);
-
-    // ---- K(c) has landed (and, for c == 0, every thread's Q row) -> S = Q K^T
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(&bar_k, ph);
-      tc_fence_after();
-      const uint32_t idesc = make_idesc_bf16_ex(128, nk16, 0);
-#pragma unroll
-      for (int kk = 0; kk < DH / 16; ++kk) {
-        const uint64_t da = make_smem_desc_sw128(smem_u32(s_q) + (kk >> 2) * 16384 + (kk & 3) * 32);
-        const uint64_t db = make_smem_desc_sw128(smem_u32(s_k) + (kk >> 2) * 8192 + (kk & 3) * 32);
-        umma_bf16<1>(tmem, da, db, idesc, kk != 0 ? 1u : 0u);
-      }
-      umma_commit(&bar_s);
-    }
-    mbar_wait(&bar_s, ph);
-    __syncwarp();
-    tc_fence_after();
-    // the K buffer is free again: K(c+1) streams in under the softmax and the P V product
-    int nk_n = 0, key0_n = 0, row_n = 0; bool own_n = false;
-    if (c + 1 < n_chunks) chunk_keys(c + 1, nk_n, key0_n, own_n, row_n);
-    if (tid == 0 && c + 1 < n_chunks) stage(s_k, own_n ? &tm_kb : &tm_ka, &bar_k, row_n);
-    __syncwarp();
-
-    // ---- softmax of this row over the chunk's keys; P -> smem
-    float corr;
-    {
-      float sv[kTcKeys];
-      {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(t_s, r0);
-        if (nk16 > 32) tmem_ld32(t_s + 32, r1);   // warp-uniform
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          sv[i] = __uint_as_float(r0[i]);
-          sv[32 + i] = nk16 > 32 ? __uint_as_float(r1[i]) : 0.f;
-        }
-      }
-      // visible keys of this row inside the chunk form an interval [j_lo, j_hi]
-      int j_lo = 0, j_hi = nk - 1;
-      if (own) {
-        j_lo = max(0, seq_lo - key0);
-        j_hi = min(nk - 1, rt - key0);
-      }
-      const unsigned span = j_hi >= j_lo ? static_cast<unsigned>(j_hi - j_lo) : 0u;
-      const bool any = j_hi >= j_lo;
-      float cmax = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < kTcKeys; ++j) {
-        bool vis = any && static_cast<unsigned>(j - j_lo) <= span;
-        if (own && p.key_valid && vis) vis = p.key_valid[key0 + j] != 0;
-        const float val = vis ? sv[j] : -INFINITY;
-        sv[j] = val;
-        cmax = fmaxf(cmax, val);
-      }
-      const float m_new = fmaxf(m_run, cmax * p.scale_log2);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      corr = exp2f(m_run - m_use);
-      m_run = m_new;
-      float csum = 0.f;
-#pragma unroll
-      for (int j8 = 0; j8 < kTcKeys / 8; ++j8) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float p0 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
-          const float p1 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
-          csum += p0 + p1;
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-          pk[e] = *reinterpret_cast<uint32_t*>(&b2);
-        }
-        if (j8 * 8 < nk16) *reinterpret_cast<uint4*>(s_p + sw128_offset(tid, j8 * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
-      l_run = l_run * corr + csum;
-    }
-
-    // ---- P is written (generic proxy -> async proxy), V(c) has landed -> Oc = P V
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(&bar_v, ph);
-      tc_fence_after();
-      const uint32_t idesc = make_idesc_bf16_ex(128, DH, 1);
-      for (int kk = 0; kk < nk16 / 16; ++kk) {
-        const uint64_t da = make_smem_desc_sw128(smem_u32(s_p) + kk * 32);
-        const uint64_t db = make_smem_desc_raw(smem_u32(s_v) + kk * 2048, 8192, 1024);
-        umma_bf16<1>(tmem + 64, da, db, idesc, kk != 0 ? 1u : 0u);
-      }
-      umma_commit(&bar_o);
-    }
-    mbar_wait(&bar_o, ph);
-    tc_fence_after();
-    // V and P buffers are free: V(c+1) streams in under the accumulation and the next S = Q K^T
-    if (tid == 0 && c + 1 < n_chunks) stage(s_v, own_n ? &tm_vb : &tm_va, &bar_v, row_n);
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < DH / 32; ++h) {
-      float t[32];
-      tmem_ld32_nowait(t_o + h * 32, t);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], corr, t[i]);
-    }
-    tc_fence_before();
-  }
-
-  // ---- normalise and write this row
-  if (row_ok) {
-    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-    __nv_bfloat16* dst = p.o + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH;
-#pragma unroll
-    for (int c8 = 0; c8 < DH / 8; ++c8) {
-      uint32_t pk[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(o[c8 * 8 + 2 * e] * inv, o[c8 * 8 + 2 * e + 1] * inv);
-        pk[e] = *reinterpret_cast<uint32_t*>(&b2);
-      }
-      *reinterpret_cast<uint4*>(dst + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 0) tmem_dealloc<1>(tmem, kTcTmemCols);
-}
 
 // ------------------------------------------------------------------------------------------------ v2: O stays in TMEM
 // Same decomposition, deeper overlap (the production kernel; the one above is kept for A/B runs, BLIM_ATTN=tc1):
@@ -315,7 +77,7 @@ constexpr int attn_tc2_smem_bytes() {
   return (DH / 64) * 16384 + 3 * (DH / 64) * 8192 + 16384 + 1024;
 }
 
-template <int DH>
+template <int DH, typename T16>
 __global__ void __launch_bounds__(kTc2Threads, 2)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_constant__ CUtensorMap tm_va,
                      const __grid_constant__ CUtensorMap tm_kb, const __grid_constant__ CUtensorMap tm_vb, const AttnParamsTc p) {
@@ -361,7 +123,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   const int rt = w.tok0 + (row_ok ? tok_local : 0);
   const int seq_lo = (row_ok && p.tok_seq_start != nullptr) ? __ldg(p.tok_seq_start + rt) : 0;
   {
-    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.q_stride + (kvh * G + head) * DH;
+    const T16* src = reinterpret_cast<const T16*>(p.q) + static_cast<size_t>(rt) * p.q_stride + (kvh * G + head) * DH;
 #pragma unroll
     for (int cc = 0; cc < DH / 16; ++cc) {
       const int c = half * (DH / 16) + cc;
@@ -410,7 +172,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
     const int nk16 = (nk + 15) & ~15;
     mbar_wait(&bar_k, static_cast<uint32_t>(c & 1));
     tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16_ex(128, nk16, 0);
+    const uint32_t idesc = make_idesc_f16kind(128, nk16, Fmt16<T16>::code, Fmt16<T16>::code, 0);
     if (lead) {
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {
@@ -534,8 +296,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
         const float p0 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
         const float p1 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
         csum += p0 + p1;
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-        pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+        pk[e] = Fmt16<T16>::pack2(p0, p1);
       }
       if (half * 32 + j8 * 8 < nk16) *reinterpret_cast<uint4*>(s_p + sw128_offset(r, half * 32 + j8 * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
@@ -548,7 +309,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
       mbar_wait(&bar_v[c & 1], static_cast<uint32_t>((c >> 1) & 1));
       __syncwarp();
       tc_fence_after();
-      const uint32_t idesc = make_idesc_bf16_ex(128, DH, 1);
+      const uint32_t idesc = make_idesc_f16kind(128, DH, Fmt16<T16>::code, Fmt16<T16>::code, 1);
       const uint32_t v_base = smem_u32(s_v) + (c & 1) * kSub * 8192;
       if (lead) {
         for (int kk = 0; kk < nk16 / 16; ++kk) {
@@ -571,7 +332,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   __syncthreads();
   const float l = s_x[0][r] + s_x[1][r];
   const float inv = l > 0.f ? 1.0f / l : 0.f;
-  __nv_bfloat16* dst = p.o + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH + half * (DH / 2);
+  T16* dst = reinterpret_cast<T16*>(p.o) + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH + half * (DH / 2);
 #pragma unroll
   for (int h = 0; h < DH / 64; ++h) {
     uint32_t raw[32];
@@ -583,8 +344,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(raw[c8 * 8 + 2 * e]) * inv, __uint_as_float(raw[c8 * 8 + 2 * e + 1]) * inv);
-          pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+          pk[e] = Fmt16<T16>::pack2(__uint_as_float(raw[c8 * 8 + 2 * e]) * inv, __uint_as_float(raw[c8 * 8 + 2 * e + 1]) * inv);
         }
         *reinterpret_cast<uint4*>(dst + h * 32 + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
@@ -601,7 +361,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
 // barrier initialisation, TMEM allocation, tensor-map prefetch, the CTA launch itself -- is a large part of its life.
 // v2p launches two CTAs per SM once and lets each walk over work items (item = work x KV head, consecutive items share the
 // prefix K/V in L2); the mbarrier phases simply keep counting chunks across items (g = chunks done so far + c).
-template <int DH>
+template <int DH, typename T16>
 __global__ void __launch_bounds__(kTc2Threads, 2)
 attention_tc2p_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_constant__ CUtensorMap tm_va,
                      const __grid_constant__ CUtensorMap tm_kb, const __grid_constant__ CUtensorMap tm_vb, const AttnParamsTc p) {
@@ -679,7 +439,7 @@ attention_tc2p_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_co
     const int nk16 = (nk + 15) & ~15;
     mbar_wait(&bar_k, static_cast<uint32_t>((g0 + c) & 1));
     tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16_ex(128, nk16, 0);
+    const uint32_t idesc = make_idesc_f16kind(128, nk16, Fmt16<T16>::code, Fmt16<T16>::code, 0);
     if (lead) {
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {
@@ -708,7 +468,7 @@ attention_tc2p_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_co
   const int rt = w.tok0 + (row_ok ? tok_local : 0);
   const int seq_lo = (row_ok && p.tok_seq_start != nullptr) ? __ldg(p.tok_seq_start + rt) : 0;
   {
-    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.q_stride + (kvh * G + head) * DH;
+    const T16* src = reinterpret_cast<const T16*>(p.q) + static_cast<size_t>(rt) * p.q_stride + (kvh * G + head) * DH;
 #pragma unroll
     for (int cc = 0; cc < DH / 16; ++cc) {
       const int c = half * (DH / 16) + cc;
@@ -822,8 +582,7 @@ attention_tc2p_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_co
         const float p0 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
         const float p1 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
         csum += p0 + p1;
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-        pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+        pk[e] = Fmt16<T16>::pack2(p0, p1);
       }
       if (half * 32 + j8 * 8 < nk16) *reinterpret_cast<uint4*>(s_p + sw128_offset(r, half * 32 + j8 * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
@@ -836,7 +595,7 @@ attention_tc2p_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_co
       mbar_wait(&bar_v[(g0 + c) & 1], static_cast<uint32_t>(((g0 + c) >> 1) & 1));
       __syncwarp();
       tc_fence_after();
-      const uint32_t idesc = make_idesc_bf16_ex(128, DH, 1);
+      const uint32_t idesc = make_idesc_f16kind(128, DH, Fmt16<T16>::code, Fmt16<T16>::code, 1);
       const uint32_t v_base = smem_u32(s_v) + ((g0 + c) & 1) * kSub * 8192;
       if (lead) {
         for (int kk = 0; kk < nk16 / 16; ++kk) {
@@ -859,7 +618,7 @@ attention_tc2p_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_co
   __syncthreads();
   const float l = s_x[0][r] + s_x[1][r];
   const float inv = l > 0.f ? 1.0f / l : 0.f;
-  __nv_bfloat16* dst = p.o + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH + half * (DH / 2);
+  T16* dst = reinterpret_cast<T16*>(p.o) + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH + half * (DH / 2);
 #pragma unroll
   for (int h = 0; h < DH / 64; ++h) {
     uint32_t raw[32];
@@ -871,8 +630,7 @@ attention_tc2p_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_co
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(raw[c8 * 8 + 2 * e]) * inv, __uint_as_float(raw[c8 * 8 + 2 * e + 1]) * inv);
-          pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+          pk[e] = Fmt16<T16>::pack2(__uint_as_float(raw[c8 * 8 + 2 * e]) * inv, __uint_as_float(raw[c8 * 8 + 2 * e + 1]) * inv);
         }
         *reinterpret_cast<uint4*>(dst + h * 32 + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
@@ -891,280 +649,6 @@ attention_tc2p_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_co
 // the TOP of round c (its K chunk was prefetched a whole round earlier) and runs under the softmax of chunk c; at the end
 // of a round only Oc = P V is issued.  All bookkeeping lives in dynamic shared memory (no static __shared__) so that two
 // CTAs of 112.6 KB still fit one SM; the host checks the occupancy and falls back to v2 otherwise.
-template <int DH>
-constexpr int attn_tc3_smem_bytes() {
-  // Q (DH/64 x 16 KB) + 2 x K + 2 x V (DH/64 x 8 KB each) + P (16 KB) + max exchange (512 B) + barriers (64 B)
-  return (DH / 64) * 16384 + 4 * (DH / 64) * 8192 + 16384 + 512 + 64;
-}
-
-template <int DH>
-__global__ void __launch_bounds__(kTc2Threads, 2)
-attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_constant__ CUtensorMap tm_va,
-                     const __grid_constant__ CUtensorMap tm_kb, const __grid_constant__ CUtensorMap tm_vb, const AttnParamsTc p) {
-  constexpr int kSub = DH / 64;
-  constexpr uint32_t kChunkBytes = kSub * 8192;
-  constexpr float kGrow = 8.0f;
-  extern __shared__ __align__(1024) uint8_t smem_tc3[];
-  uint8_t* s_q = smem_tc3;
-  uint8_t* s_k = s_q + kSub * 16384;           // two stages
-  uint8_t* s_v = s_k + 2 * kSub * 8192;        // two stages
-  uint8_t* s_p = s_v + 2 * kSub * 8192;
-  __nv_bfloat16* s_mx = reinterpret_cast<__nv_bfloat16*>(s_p + 16384);   // [2][128] row maxima of the two half-row threads
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 16384 + 512);
-  uint64_t* bar_s = bars;        // [2]
-  uint64_t* bar_k = bars + 2;    // [2]
-  uint64_t* bar_v = bars + 4;    // [2]
-  uint64_t* bar_o = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-
-  const AttnWorkTc w = p.works[blockIdx.x];
-  const int kvh = blockIdx.y;
-  const int G = p.group;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int r = tid & 127, half = tid >> 7;
-
-  if (tid == 0) {
-    if (smem_u32(smem_tc3) & 1023u) __trap();   // the swizzled tiles need a 1024-byte aligned base
-    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
-    fence_barrier_init();
-    tma_prefetch_desc(&tm_ka);
-    tma_prefetch_desc(&tm_va);
-    tma_prefetch_desc(&tm_kb);
-    tma_prefetch_desc(&tm_vb);
-  }
-  if (warp == 0) tmem_alloc<1>(tmem_slot, kTcTmemCols);
-
-  const int tok_local = r / G, head = r - tok_local * G;
-  const bool row_ok = tok_local < w.n_tok;
-  const int rt = w.tok0 + (row_ok ? tok_local : 0);
-  const int seq_lo = (row_ok && p.tok_seq_start != nullptr) ? __ldg(p.tok_seq_start + rt) : 0;
-  {
-    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.q_stride + (kvh * G + head) * DH;
-#pragma unroll
-    for (int cc = 0; cc < DH / 16; ++cc) {
-      const int c = half * (DH / 16) + cc;
-      cp_async16(s_q + (c >> 3) * 16384 + sw128_offset(r, (c & 7) * 8), src + c * 8, row_ok ? 16 : 0);
-    }
-    cp_async_commit();
-  }
-
-  const int n_a = (w.a_len + kTcKeys - 1) / kTcKeys;
-  const int own_len = w.tok0 + w.n_tok - w.kb0;
-  const int n_chunks = n_a + (own_len + kTcKeys - 1) / kTcKeys;
-
-  auto chunk_keys = [&](int c, int& nk, int& key0, bool& own, int& tm_row) {
-    if (c < n_a) {
-      own = false;
-      key0 = c * kTcKeys;
-      nk = min(kTcKeys, w.a_len - key0);
-      tm_row = p.a_row0 + w.a_start + key0;
-    } else {
-      own = true;
-      key0 = w.kb0 + (c - n_a) * kTcKeys;
-      nk = min(kTcKeys, w.tok0 + w.n_tok - key0);
-      tm_row = p.b_row0 + key0 + w.b_off;
-    }
-  };
-  auto stage = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tm_row) {
-    mbar_arrive_expect_tx(bar, kChunkBytes);
-#pragma unroll
-    for (int sub = 0; sub < kSub; ++sub) tma_load_2d(dst + sub * 8192, tm, bar, kvh * DH + sub * 64, tm_row);
-  };
-  auto stage_k = [&](int c) {
-    int nk, key0, row; bool own;
-    chunk_keys(c, nk, key0, own, row);
-    stage(s_k + (c & 1) * kSub * 8192, own ? &tm_kb : &tm_ka, &bar_k[c & 1], row);
-  };
-  auto stage_v = [&](int c) {
-    int nk, key0, row; bool own;
-    chunk_keys(c, nk, key0, own, row);
-    stage(s_v + (c & 1) * kSub * 8192, own ? &tm_vb : &tm_va, &bar_v[c & 1], row);
-  };
-  auto issue_s = [&](int c, uint32_t tmem) {   // S[c & 1] = Q K(c)^T (tid 0 only)
-    int nk, key0, row; bool own;
-    chunk_keys(c, nk, key0, own, row);
-    const int nk16 = (nk + 15) & ~15;
-    mbar_wait(&bar_k[c & 1], static_cast<uint32_t>((c >> 1) & 1));
-    tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16_ex(128, nk16, 0);
-    const uint32_t k_base = smem_u32(s_k) + (c & 1) * kSub * 8192;
-#pragma unroll
-    for (int kk = 0; kk < DH / 16; ++kk) {
-      const uint64_t da = make_smem_desc_sw128(smem_u32(s_q) + (kk >> 2) * 16384 + (kk & 3) * 32);
-      const uint64_t db = make_smem_desc_sw128(k_base + (kk >> 2) * 8192 + (kk & 3) * 32);
-      umma_bf16<1>(tmem + (c & 1) * 64, da, db, idesc, kk != 0 ? 1u : 0u);
-    }
-    umma_commit(&bar_s[c & 1]);
-  };
-
-  cp_async_wait<0>();
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();   // barriers initialised, TMEM allocated, Q staged
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  if (tid == 0) {
-    stage_k(0);
-    stage_v(0);
-    if (n_chunks > 1) { stage_k(1); stage_v(1); }
-    issue_s(0, tmem);
-  }
-  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  const uint32_t t_o = t_row + 128 + half * (DH / 2);      // this thread's DH/2 O columns (S0: [0,64), S1: [64,128))
-
-  float m_ref = -INFINITY, l_part = 0.f;
-
-  for (int c = 0; c < n_chunks; ++c) {
-    int nk, key0, tm_row_unused; bool own;
-    chunk_keys(c, nk, key0, own, tm_row_unused);
-    const int nk16 = (nk + 15) & ~15;
-
-    mbar_wait(&bar_s[c & 1], static_cast<uint32_t>((c >> 1) & 1));
-    if (tid == 0) {
-      // S(c) is complete: its K stage is free again, and S(c+1) (other accumulator, K prefetched a round ago) can start now
-      if (c + 1 < n_chunks) issue_s(c + 1, tmem);
-      if (c + 2 < n_chunks) stage_k(c + 2);
-    }
-    __syncwarp();
-    tc_fence_after();
-    float sv[32];
-    if (half * 32 < nk16) {   // warp-uniform
-      uint32_t raw[32];
-      tmem_ld32(t_row + (c & 1) * 64 + half * 32, raw);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(raw[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) sv[i] = 0.f;
-    }
-    float cmax = -INFINITY;
-    if (!own && nk == kTcKeys) {   // CTA-uniform fast path: a full chunk of the shared prefix, every key visible
-#pragma unroll
-      for (int i = 0; i < 32; ++i) cmax = fmaxf(cmax, sv[i]);
-    } else {
-      int j_lo = 0, j_hi = nk - 1;
-      if (own) {
-        j_lo = max(0, seq_lo - key0);
-        j_hi = min(nk - 1, rt - key0);
-      }
-      // visible keys among this thread's 32 as a bit mask: [j_lo, j_hi] clipped to the half's window
-      const int lo = max(j_lo - half * 32, 0), hi = min(j_hi - half * 32, 31);
-      uint32_t vmask = (hi >= lo) ? ((0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo)) : 0u;
-      if (own && p.key_valid != nullptr && vmask != 0u) {
-        const uint8_t* kv = p.key_valid + key0 + half * 32;
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (((vmask >> i) & 1u) && kv[i] == 0) vmask &= ~(1u << i);
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float val = ((vmask >> i) & 1u) ? sv[i] : -INFINITY;
-        sv[i] = val;
-        cmax = fmaxf(cmax, val);
-      }
-    }
-    s_mx[half * 128 + r] = __float2bfloat16(cmax);   // both threads of the row use the same (bf16-rounded) pair of maxima
-    tc_fence_before();
-    __syncthreads();   // [A]
-    const float cmax_s = fmaxf(__bfloat162float(s_mx[r]), __bfloat162float(s_mx[128 + r])) * p.scale_log2;
-
-    if (c > 0) {
-      mbar_wait(bar_o, static_cast<uint32_t>((c - 1) & 1));
-      if (tid == 0 && c + 1 < n_chunks) stage_v(c + 1);   // its stage was read by chunk c-1
-      __syncwarp();
-      tc_fence_after();
-    }
-    float corr = 1.f;
-    bool grow = false;
-    if (c == 0) {
-      m_ref = cmax_s;
-    } else if (cmax_s > m_ref + kGrow) {
-      grow = true;
-      corr = exp2f(m_ref - cmax_s);
-      m_ref = cmax_s;
-      l_part *= corr;
-    }
-    if (__any_sync(0xffffffffu, grow)) {
-#pragma unroll
-      for (int h = 0; h < DH / 64; ++h) {
-        uint32_t raw[32];
-        tmem_ld32(t_o + h * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
-        tmem_st32(t_o + h * 32, raw);
-      }
-      tmem_st_wait();
-    }
-    const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-    float csum = 0.f;
-#pragma unroll
-    for (int j8 = 0; j8 < 4; ++j8) {
-      uint32_t pk[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float p0 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
-        const float p1 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
-        csum += p0 + p1;
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-        pk[e] = *reinterpret_cast<uint32_t*>(&b2);
-      }
-      if (half * 32 + j8 * 8 < nk16) *reinterpret_cast<uint4*>(s_p + sw128_offset(r, half * 32 + j8 * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    }
-    l_part += csum;
-
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();   // [B] P written, O rescaled
-    if (tid == 0) {
-      mbar_wait(&bar_v[c & 1], static_cast<uint32_t>((c >> 1) & 1));
-      tc_fence_after();
-      const uint32_t idesc = make_idesc_bf16_ex(128, DH, 1);
-      const uint32_t v_base = smem_u32(s_v) + (c & 1) * kSub * 8192;
-      for (int kk = 0; kk < nk16 / 16; ++kk) {
-        const uint64_t da = make_smem_desc_sw128(smem_u32(s_p) + kk * 32);
-        const uint64_t db = make_smem_desc_raw(v_base + kk * 2048, 8192, 1024);
-        umma_bf16<1>(tmem + 128, da, db, idesc, (c > 0 || kk != 0) ? 1u : 0u);
-      }
-      umma_commit(bar_o);
-    }
-  }
-
-  // ---- O / l -> bf16   (the P tile is free: reuse it to add the two half-row sums)
-  mbar_wait(bar_o, static_cast<uint32_t>((n_chunks - 1) & 1));
-  __syncwarp();
-  tc_fence_after();
-  float* s_l = reinterpret_cast<float*>(s_p);
-  s_l[half * 128 + r] = l_part;
-  __syncthreads();
-  const float l = s_l[r] + s_l[128 + r];
-  const float inv = l > 0.f ? 1.0f / l : 0.f;
-  __nv_bfloat16* dst = p.o + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH + half * (DH / 2);
-#pragma unroll
-  for (int h = 0; h < DH / 64; ++h) {
-    uint32_t raw[32];
-    tmem_ld32(t_o + h * 32, raw);
-    tmem_ld_wait();
-    if (row_ok) {
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(raw[c8 * 8 + 2 * e]) * inv, __uint_as_float(raw[c8 * 8 + 2 * e + 1]) * inv);
-          pk[e] = *reinterpret_cast<uint32_t*>(&b2);
-        }
-        *reinterpret_cast<uint4*>(dst + h * 32 + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 0) tmem_dealloc<1>(tmem, kTcTmemCols);
-}
-
 // ------------------------------------------------------------------------------------------------ v4: dedicated issue warp
 // Same data flow as v3 (two S accumulators in TMEM, K and V double-buffered), but every TMA and tcgen05.mma is issued by a
 // NINTH warp that does nothing else.  In v2 / v3 thread 0 issues them between its own softmax work, so warp 0 executes
@@ -1191,7 +675,7 @@ constexpr int attn_tc4_smem_bytes() {
 // barrier of the two warps (w, w + 4) that share TMEM lane quadrant q = w & 3
 __device__ __forceinline__ void softmax_pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
 
-template <int DH>
+template <int DH, typename T16>
 __global__ void __launch_bounds__(kTc4Threads, 2)
 attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_constant__ CUtensorMap tm_va,
                      const __grid_constant__ CUtensorMap tm_kb, const __grid_constant__ CUtensorMap tm_vb, const AttnParamsTc p) {
@@ -1242,7 +726,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   const int rt = w.tok0 + (row_ok ? tok_local : 0);
   const int seq_lo = (row_ok && p.tok_seq_start != nullptr) ? __ldg(p.tok_seq_start + rt) : 0;
   if (!issuer) {
-    const __nv_bfloat16* src = p.q + static_cast<size_t>(rt) * p.q_stride + (kvh * G + head) * DH;
+    const T16* src = reinterpret_cast<const T16*>(p.q) + static_cast<size_t>(rt) * p.q_stride + (kvh * G + head) * DH;
 #pragma unroll
     for (int cc = 0; cc < DH / 16; ++cc) {
       const int c = half * (DH / 16) + cc;
@@ -1294,7 +778,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
     const int nk16 = (nk + 15) & ~15;
     mbar_wait(&bar_k[c & 1], static_cast<uint32_t>((c >> 1) & 1));
     tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16_ex(128, nk16, 0);
+    const uint32_t idesc = make_idesc_f16kind(128, nk16, Fmt16<T16>::code, Fmt16<T16>::code, 0);
     const uint32_t k_base = smem_u32(s_k) + (c & 1) * kSub * 8192;
     if (lead) {
 #pragma unroll
@@ -1338,7 +822,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
         mbar_wait(bar_p, static_cast<uint32_t>(c & 1));                  // P(c) written, O rescaled
         mbar_wait(&bar_v[c & 1], static_cast<uint32_t>((c >> 1) & 1));
         tc_fence_after();
-        const uint32_t idesc = make_idesc_bf16_ex(128, DH, 1);
+        const uint32_t idesc = make_idesc_f16kind(128, DH, Fmt16<T16>::code, Fmt16<T16>::code, 1);
         const uint32_t v_base = smem_u32(s_v) + (c & 1) * kSub * 8192;
         if (lead) {
           if (nk16 == kTcKeys) {
@@ -1474,8 +958,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
         const float p0 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e], p.scale_log2, -m_use));
         const float p1 = fast_exp2(fmaf(sv[j8 * 8 + 2 * e + 1], p.scale_log2, -m_use));
         csum += p0 + p1;
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-        pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+        pk[e] = Fmt16<T16>::pack2(p0, p1);
       }
       if (half * 32 + j8 * 8 < nk16)
         *reinterpret_cast<uint4*>(s_p + (kPDouble ? (c & 1) * 16384 : 0) + sw128_offset(r, half * 32 + j8 * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -1497,7 +980,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
   softmax_pair_sync(warp & 3);
   const float l = s_l[r] + s_l[128 + r];
   const float inv = l > 0.f ? 1.0f / l : 0.f;
-  __nv_bfloat16* dst = p.o + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH + half * (DH / 2);
+  T16* dst = reinterpret_cast<T16*>(p.o) + static_cast<size_t>(rt) * p.n_q + (kvh * G + head) * DH + half * (DH / 2);
 #pragma unroll
   for (int h = 0; h < DH / 64; ++h) {
     uint32_t raw[32];
@@ -1509,8 +992,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_con
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(raw[c8 * 8 + 2 * e]) * inv, __uint_as_float(raw[c8 * 8 + 2 * e + 1]) * inv);
-          pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+          pk[e] = Fmt16<T16>::pack2(__uint_as_float(raw[c8 * 8 + 2 * e]) * inv, __uint_as_float(raw[c8 * 8 + 2 * e + 1]) * inv);
         }
         *reinterpret_cast<uint4*>(dst + h * 32 + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
@@ -1566,60 +1048,63 @@ struct AttnTcMaps {
   CUtensorMap ka, va, kb, vb;
 };
 
-template <int DH>
+enum : int { kAttnPersistent = 5, kAttnPerItem = 2, kAttnIssueWarp = 4 };   // attention_tc2p / _tc2 / _tc4
+
+// cudaFuncSetAttribute once per (kernel instantiation, device): function attributes are per device
+template <class Kern>
+inline cudaError_t attn_set_smem(Kern kern, int bytes, bool max_carveout, bool* done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (done[dev & 63]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && max_carveout) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess) done[dev & 63] = true;
+  return e;
+}
+
+template <int DH, typename T16>
 inline cudaError_t launch_attention_tc2_impl(const AttnTcMaps& m, const AttnParamsTc& p, dim3 grid, cudaStream_t stream) {
-  static bool set = false;
-  if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc2_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc2_smem_bytes<DH>());
-    if (e != cudaSuccess) return e;
-    set = true;
-  }
-  attention_tc2_kernel<DH><<<grid, kTc2Threads, attn_tc2_smem_bytes<DH>(), stream>>>(m.ka, m.va, m.kb, m.vb, p);
+  static bool done[64] = {};
+  cudaError_t e = attn_set_smem(attention_tc2_kernel<DH, T16>, attn_tc2_smem_bytes<DH>(), false, done);
+  if (e != cudaSuccess) return e;
+  attention_tc2_kernel<DH, T16><<<grid, kTc2Threads, attn_tc2_smem_bytes<DH>(), stream>>>(m.ka, m.va, m.kb, m.vb, p);
   return cudaGetLastError();
 }
 
-// v3 needs two 112.6 KB CTAs per SM; returns cudaErrorLaunchOutOfResources (caller falls back to v2) when they do not fit.
-template <int DH>
-inline cudaError_t launch_attention_tc3_impl(const AttnTcMaps& m, const AttnParamsTc& p, dim3 grid, cudaStream_t stream) {
-  static int state = 0;  // 0 = unknown, 1 = usable, -1 = does not fit twice
-  if (state == 0) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc3_smem_bytes<DH>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc3_kernel<DH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    // two CTAs per SM?  (the occupancy API under-reports with large dynamic shared memory, so the two limits are checked
-    // directly: 228 KB of shared memory per SM incl. 1 KB reserved per CTA, 64 K registers allocated in units of 8 per thread)
-    cudaFuncAttributes fa;
-    int blocks = 0, dev = 0, smem_sm = 0, regs_sm = 0;
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, attention_tc3_kernel<DH>);
-    if (e == cudaSuccess) e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
-    if (e == cudaSuccess) {
-      const int smem_cta = ((attn_tc3_smem_bytes<DH>() + static_cast<int>(fa.sharedSizeBytes) + 127) & ~127) + 1024;
-      const int regs_cta = kTc2Threads * ((fa.numRegs + 7) & ~7);
-      blocks = std::min(smem_sm / smem_cta, regs_sm / regs_cta);
-    } else {
-      cudaGetLastError();
-    }
-    state = (e == cudaSuccess && blocks >= 2) ? 1 : -1;
-    if (getenv("BLIM_DEBUG")) fprintf(stderr, "[blim] attention v3 (head_dim %d): %d CTA(s) per SM with %d B dynamic smem -> %s\n", DH, blocks,
-                                      attn_tc3_smem_bytes<DH>(), state > 0 ? "used" : "falling back to v2");
-  }
-  if (state < 0) return cudaErrorLaunchOutOfResources;
-  attention_tc3_kernel<DH><<<grid, kTc2Threads, attn_tc3_smem_bytes<DH>(), stream>>>(m.ka, m.va, m.kb, m.vb, p);
+// persistent v2: two CTAs per SM walk over the work items (work x KV head)
+template <int DH, typename T16>
+inline cudaError_t launch_attention_tc2p_impl(const AttnTcMaps& m, const AttnParamsTc& p, int n_works, int n_kv_heads, cudaStream_t stream) {
+  static bool done[64] = {};
+  cudaError_t e = attn_set_smem(attention_tc2p_kernel<DH, T16>, attn_tc2_smem_bytes<DH>(), false, done);
+  if (e != cudaSuccess) return e;
+  AttnParamsTc pp = p;
+  pp.n_works = n_works;
+  pp.n_kv_heads = n_kv_heads;
+  int dev = 0, n_sm = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm = 148;
+  const int items = n_works * n_kv_heads;
+  dim3 pgrid(static_cast<unsigned>(std::min(items, 2 * n_sm)));
+  attention_tc2p_kernel<DH, T16><<<pgrid, kTc2Threads, attn_tc2_smem_bytes<DH>(), stream>>>(m.ka, m.va, m.kb, m.vb, pp);
   return cudaGetLastError();
 }
 
 // v4 needs two 112.7 KB CTAs of 288 threads per SM; returns cudaErrorLaunchOutOfResources (caller falls back) otherwise.
-template <int DH>
+template <int DH, typename T16>
 inline cudaError_t launch_attention_tc4_impl(const AttnTcMaps& m, const AttnParamsTc& p, dim3 grid, cudaStream_t stream) {
-  static int state = 0;
-  if (state == 0) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc4_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc4_smem_bytes<DH>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc4_kernel<DH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  static int state[64] = {};   // per device: 0 = unknown, 1 = usable, -1 = does not fit twice
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  int& st = state[dev & 63];
+  if (st == 0) {
+    e = cudaFuncSetAttribute(attention_tc4_kernel<DH, T16>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc4_smem_bytes<DH>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc4_kernel<DH, T16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // two CTAs per SM?  (the occupancy API under-reports with large dynamic shared memory, so the two limits are checked
+    // directly: 228 KB of shared memory per SM incl. 1 KB reserved per CTA, 64 K registers allocated in units of 8 per thread)
     cudaFuncAttributes fa;
-    int blocks = 0, dev = 0, smem_sm = 0, regs_sm = 0;
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, attention_tc4_kernel<DH>);
-    if (e == cudaSuccess) e = cudaGetDevice(&dev);
+    int blocks = 0, smem_sm = 0, regs_sm = 0;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, attention_tc4_kernel<DH, T16>);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
     if (e == cudaSuccess) {
@@ -1629,88 +1114,31 @@ inline cudaError_t launch_attention_tc4_impl(const AttnTcMaps& m, const AttnPara
     } else {
       cudaGetLastError();
     }
-    state = (e == cudaSuccess && blocks >= 2) ? 1 : -1;
+    st = (e == cudaSuccess && blocks >= 2) ? 1 : -1;
     if (getenv("BLIM_DEBUG")) fprintf(stderr, "[blim] attention v4 (head_dim %d): %d CTA(s) per SM with %d B dynamic smem -> %s\n", DH, blocks,
-                                      attn_tc4_smem_bytes<DH>(), state > 0 ? "used" : "falling back");
+                                      attn_tc4_smem_bytes<DH>(), st > 0 ? "used" : "falling back");
   }
-  if (state < 0) return cudaErrorLaunchOutOfResources;
-  attention_tc4_kernel<DH><<<grid, kTc4Threads, attn_tc4_smem_bytes<DH>(), stream>>>(m.ka, m.va, m.kb, m.vb, p);
+  if (st < 0) return cudaErrorLaunchOutOfResources;
+  attention_tc4_kernel<DH, T16><<<grid, kTc4Threads, attn_tc4_smem_bytes<DH>(), stream>>>(m.ka, m.va, m.kb, m.vb, p);
   return cudaGetLastError();
 }
 
+// T16 = operand format of Q / K / V / P / O.  version: kAttnPersistent (scoring path), kAttnPerItem, kAttnIssueWarp
+// (head_dim 64 only: at 128 its 96-register budget spills; falls back to the per-item kernel when two CTAs do not fit).
+template <typename T16>
 inline cudaError_t launch_attention_tc(const AttnTcMaps& m, const AttnParamsTc& p, int n_works, int n_kv_heads, int head_dim,
-                                       cudaStream_t stream, int version = 2) {
+                                       cudaStream_t stream, int version = kAttnPerItem) {
   if (n_works <= 0) return cudaSuccess;
+  if (head_dim != 64 && head_dim != 128) return cudaErrorInvalidValue;
   dim3 grid(static_cast<unsigned>(n_works), static_cast<unsigned>(n_kv_heads));
-  if (version == 4) {
-    cudaError_t e = head_dim == 128 ? launch_attention_tc4_impl<128>(m, p, grid, stream)
-                  : head_dim == 64 ? launch_attention_tc4_impl<64>(m, p, grid, stream) : cudaErrorInvalidValue;
+  if (version == kAttnIssueWarp && head_dim == 64) {
+    cudaError_t e = launch_attention_tc4_impl<64, T16>(m, p, grid, stream);
     if (e != cudaErrorLaunchOutOfResources) return e;
-    version = 2;
   }
-  if (version == 3) {
-    cudaError_t e = head_dim == 128 ? launch_attention_tc3_impl<128>(m, p, grid, stream)
-                  : head_dim == 64 ? launch_attention_tc3_impl<64>(m, p, grid, stream) : cudaErrorInvalidValue;
-    if (e != cudaErrorLaunchOutOfResources) return e;
-    version = 2;  // two CTAs per SM do not fit: the single-buffered kernel is the better choice
-  }
-  if (version == 5) {   // persistent v2
-    AttnParamsTc pp = p;
-    pp.n_works = n_works;
-    pp.n_kv_heads = n_kv_heads;
-    static int n_sm = 0;
-    if (n_sm == 0) {
-      int dev = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm = 148;
-    }
-    const int items = n_works * n_kv_heads;
-    dim3 pgrid(static_cast<unsigned>(std::min(items, 2 * n_sm)));
-    if (head_dim == 128) {
-      static bool set = false;
-      if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc2p_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc2_smem_bytes<128>());
-        if (e != cudaSuccess) return e;
-        set = true;
-      }
-      attention_tc2p_kernel<128><<<pgrid, kTc2Threads, attn_tc2_smem_bytes<128>(), stream>>>(m.ka, m.va, m.kb, m.vb, pp);
-    } else if (head_dim == 64) {
-      static bool set = false;
-      if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc2p_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc2_smem_bytes<64>());
-        if (e != cudaSuccess) return e;
-        set = true;
-      }
-      attention_tc2p_kernel<64><<<pgrid, kTc2Threads, attn_tc2_smem_bytes<64>(), stream>>>(m.ka, m.va, m.kb, m.vb, pp);
-    } else {
-      return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
-  }
-  if (version == 2) {
-    if (head_dim == 128) return launch_attention_tc2_impl<128>(m, p, grid, stream);
-    if (head_dim == 64) return launch_attention_tc2_impl<64>(m, p, grid, stream);
-    return cudaErrorInvalidValue;
-  }
-  if (head_dim == 128) {
-    static bool set = false;
-    if (!set) {
-      cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc_smem_bytes<128>());
-      if (e != cudaSuccess) return e;
-      set = true;
-    }
-    attention_tc_kernel<128><<<grid, kTcThreads, attn_tc_smem_bytes<128>(), stream>>>(m.ka, m.va, m.kb, m.vb, p);
-  } else if (head_dim == 64) {
-    static bool set = false;
-    if (!set) {
-      cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc_smem_bytes<64>());
-      if (e != cudaSuccess) return e;
-      set = true;
-    }
-    attention_tc_kernel<64><<<grid, kTcThreads, attn_tc_smem_bytes<64>(), stream>>>(m.ka, m.va, m.kb, m.vb, p);
-  } else {
-    return cudaErrorInvalidValue;
-  }
-  return cudaGetLastError();
+  if (version == kAttnPersistent)
+    return head_dim == 128 ? launch_attention_tc2p_impl<128, T16>(m, p, n_works, n_kv_heads, stream)
+                           : launch_attention_tc2p_impl<64, T16>(m, p, n_works, n_kv_heads, stream);
+  return head_dim == 128 ? launch_attention_tc2_impl<128, T16>(m, p, grid, stream) : launch_attention_tc2_impl<64, T16>(m, p, grid, stream);
 }
 
 }  // namespace blim

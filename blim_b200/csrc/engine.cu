@@ -31,7 +31,7 @@
 #include "umma_probe.cuh"
 
 using namespace blim;
-typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat16 bf16;   // the embedding table and the bf16 tensors of the compat entry points; GEMM operands are act_t (act_type.cuh)
 
 static std::string g_create_error;
 
@@ -155,10 +155,10 @@ struct blim_engine {
 
   // workspaces
   DevBuf x, xn, q, attn, k_own, v_own, act, kp, vp, prefix_last, vis, proj_tmp, lm_a, pred, partial, tgt_logit, logp, uniq_scores;
+  DevBuf io_in, io_out;      // bf16 <-> activation-format staging of the compat entry points (allocated on first use)
   DevBuf vis_in, d_vis_idx;  // projector input staging for non-contiguous video sets (gathered feature rows + their indices)
   DevBuf d_tok_slot, d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
-  bool attn_tc = true;  // tcgen05 attention (BLIM_ATTN=mma selects the mma.sync kernel, tc1 the first tcgen05 kernel)
-  int attn_tc_version = 5;  // 5 = persistent v2 (default), 2 = v2, 1 / 3 / 4 = A/B variants (BLIM_ATTN=tc2p|tc2|tc1|tc3|tc4)
+  int attn_version = kAttnPersistent;  // BLIM_ATTN=tc2 selects the per-item kernel (A/B against the persistent default)
   uint8_t* arena = nullptr;  // pinned staging arena for scheduler metadata (see upload())
   size_t arena_cap = 0, arena_off = 0;
   bool arena_disabled = false;
@@ -229,27 +229,28 @@ template <int G> struct EpiProf<EpiResidT<G>> { static int sub(const blim_engine
 template <> struct EpiProf<EpiResidNorm> { static int sub(const blim_engine* e, int K) { return K == e->I ? kProfDown : kProfOProj; } };
 
 template <class Epi>
-static int gemm(blim_engine* e, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const typename Epi::Params& p,
-                cudaStream_t st) {
+// A = activation operand, W = weight operand, both in the operand format act_t.
+static int gemm(blim_engine* e, const void* A, int lda, const void* W, int ldw, int M, int N, int K, const typename Epi::Params& p,
+                cudaStream_t st, int b_fmt = kActFmt, int a_fmt = kActFmt) {
   if (M <= 0) return 0;
   e->tic(0, st, EpiProf<Epi>::sub(e, K), 2.0 * M * static_cast<double>(N) * K);
-  cudaError_t r = launch_gemm<Epi>(e->gemm, A, lda, W, ldw, M, N, K, p, st);
+  cudaError_t r = launch_gemm<Epi>(e->gemm, A, lda, W, ldw, M, N, K, p, st, a_fmt, b_fmt);
   e->toc(st);
   if (r != cudaSuccess) return e->fail_cuda("tcgen05 gemm launch", r);
   e->flops += 2.0 * M * static_cast<double>(N) * K;
   return 0;
 }
 
-static int gemm_qkv(blim_engine* e, const bf16* A, const LayerW& w, int M, bf16* q_out, bf16* k_out, bf16* v_out, const int* pos,
+static int gemm_qkv(blim_engine* e, const act_t* A, const LayerW& w, int M, act_t* q_out, act_t* k_out, act_t* v_out, const int* pos,
                     const int* kv_slot, const float* rstd, cudaStream_t st) {
   if (e->DH == 128) {
     EpiQkvRope<128>::Params p{q_out, k_out, v_out, w.b_qkv.as<float>(), pos, kv_slot, e->rope_cos.as<float>(), e->rope_sin.as<float>(),
                               e->NQ, e->NKVD, e->rope_n, rstd};
-    return gemm<EpiQkvRope<128>>(e, A, e->H, w.w_qkv.as<bf16>(), e->H, M, e->NQKV, e->H, p, st);
+    return gemm<EpiQkvRope<128>>(e, A, e->H, w.w_qkv.as<act_t>(), e->H, M, e->NQKV, e->H, p, st);
   }
   EpiQkvRope<64>::Params p{q_out, k_out, v_out, w.b_qkv.as<float>(), pos, kv_slot, e->rope_cos.as<float>(), e->rope_sin.as<float>(),
                            e->NQ, e->NKVD, e->rope_n, rstd};
-  return gemm<EpiQkvRope<64>>(e, A, e->H, w.w_qkv.as<bf16>(), e->H, M, e->NQKV, e->H, p, st);
+  return gemm<EpiQkvRope<64>>(e, A, e->H, w.w_qkv.as<act_t>(), e->H, M, e->NQKV, e->H, p, st);
 }
 
 // ------------------------------------------------------------------------------------------------ create / destroy
@@ -261,7 +262,7 @@ extern "C" void blim_destroy(blim_engine* e) {
   DevBuf* bufs[] = {&e->embed, &e->lm_head, &e->visual_head, &e->norm, &e->rope_cos, &e->rope_sin, &e->feats, &e->vocab, &e->tvg_vis,
                     &e->x, &e->xn, &e->q, &e->attn, &e->k_own, &e->v_own, &e->act, &e->kp, &e->vp, &e->prefix_last, &e->vis, &e->vis_in, &e->d_vis_idx,
                     &e->proj_tmp, &e->lm_a, &e->pred, &e->partial, &e->tgt_logit, &e->logp, &e->uniq_scores, &e->d_tok_src,
-                    &e->d_tok_pos, &e->d_key_valid, &e->d_seqs, &e->d_works, &e->d_idx, &e->d_targets, &e->d_row_off, &e->d_map, &e->d_seq_start, &e->ssq, &e->rstd, &e->d_tok_slot};
+                    &e->d_tok_pos, &e->d_key_valid, &e->d_seqs, &e->d_works, &e->d_idx, &e->d_targets, &e->d_row_off, &e->d_map, &e->d_seq_start, &e->ssq, &e->rstd, &e->d_tok_slot, &e->io_in, &e->io_out};
   for (DevBuf* b : bufs) b->release();
   for (LayerW& l : e->layers) {
     l.w_qkv.release(); l.w_o.release(); l.w_gu.release(); l.w_down.release(); l.b_qkv.release(); l.ln1.release(); l.ln2.release();
@@ -303,8 +304,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
   e->gemm.device = device;
   {
     const char* a = getenv("BLIM_ATTN");
-    e->attn_tc = !(a && std::string(a) == "mma");
-    e->attn_tc_version = (a && std::string(a) == "tc1") ? 1 : (a && std::string(a) == "tc3") ? 3 : (a && std::string(a) == "tc4") ? 4 : (a && std::string(a) == "tc2") ? 2 : 5;
+    e->attn_version = (a && std::string(a) == "tc2") ? kAttnPerItem : kAttnPersistent;
     const char* rs = getenv("BLIM_ROOT");
     e->root_share = !(rs && std::string(rs) == "0");
     const char* f = getenv("BLIM_FUSE_NORM");
@@ -335,7 +335,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
       {&e->prefix_last, static_cast<size_t>(e->Umax) * e->H * 4}, {&e->vis, P * e->H * 2}, {&e->vis_in, P * e->MM * 2}, {&e->d_vis_idx, P * 4}, {&e->proj_tmp, T * e->H * 2},
       {&e->lm_a, T * e->H * 2}, {&e->pred, T * e->MM * 2}, {&e->tgt_logit, T * 4}, {&e->logp, T * 4},
       {&e->d_tok_src, T * 4}, {&e->d_tok_pos, T * 4}, {&e->d_key_valid, T}, {&e->d_seqs, T * sizeof(AttnSeq)},
-      {&e->d_works, (T * e->G / kAttnRows + T + 1) * sizeof(AttnWorkTc)}, {&e->d_idx, T * 4}, {&e->d_targets, T * 4},
+      {&e->d_works, (T * e->G / 64 + T + 1) * sizeof(AttnWorkTc)}, {&e->d_idx, T * 4}, {&e->d_targets, T * 4},
       {&e->d_row_off, (T + 1) * 4}, {&e->d_seq_start, T * 4}, {&e->ssq, T * 2 * static_cast<size_t>((e->H + kBN - 1) / kBN) * 4}, {&e->rstd, T * 4}, {&e->d_tok_slot, T * 4}};
   for (auto& a : allocs) {
     cudaError_t r = a.b->reserve(a.bytes);
@@ -359,12 +359,24 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
 }
 
 // ------------------------------------------------------------------------------------------------ weights
-static int repack_bf16(blim_engine* e, DevBuf& dst, size_t dst_rows, const void* src, int dtype, int rows, int cols, int dst_row0,
-                       int interleave, int half, cudaStream_t st) {
+// GEMM weights go to the tensor-core operand format (act_t, see act_type.cuh: both operands of a kind::f16 MMA must share
+// one format); T = bf16 keeps the checkpoint's format (the embedding table, which is gathered, never multiplied).
+template <typename T>
+static int repack_w(blim_engine* e, DevBuf& dst, size_t dst_rows, const void* src, int dtype, int rows, int cols, int dst_row0,
+                    int interleave, int half, cudaStream_t st) {
   CKE(dst.reserve(dst_rows * cols * 2));
   const size_t n = static_cast<size_t>(rows) * cols;
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
-  repack_rows_bf16_kernel<<<blocks, 256, 0, st>>>(dst.as<bf16>(), src, dtype, rows, cols, dst_row0, interleave, half);
+  repack_rows_16_kernel<T><<<blocks, 256, 0, st>>>(dst.as<T>(), src, dtype, rows, cols, dst_row0, interleave, half);
+  CKL();
+  return 0;
+}
+// same for activation-format destinations (video features: the A operand of the projector)
+static int repack_act(blim_engine* e, DevBuf& dst, size_t dst_rows, const void* src, int dtype, int rows, int cols, cudaStream_t st) {
+  CKE(dst.reserve(dst_rows * cols * 2));
+  const size_t n = static_cast<size_t>(rows) * cols;
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
+  repack_rows_16_kernel<act_t><<<blocks, 256, 0, st>>>(dst.as<act_t>(), src, dtype, rows, cols, 0, 0, 0);
   CKL();
   return 0;
 }
@@ -391,15 +403,15 @@ extern "C" int blim_load_weight(blim_engine* e, const char* name_c, const void* 
   e->weights_loaded++;
   if (name == "model.embed_tokens.weight") {
     if (!is2(V, H)) return shape_err();
-    return repack_bf16(e, e->embed, V, src, dtype, V, H, 0, 0, 0, st);
+    return repack_w<bf16>(e, e->embed, V, src, dtype, V, H, 0, 0, 0, st);
   }
   if (name == "lm_head.weight") {
     if (!is2(V, H)) return shape_err();
-    return repack_bf16(e, e->lm_head, V, src, dtype, V, H, 0, 0, 0, st);
+    return repack_w<act_t>(e, e->lm_head, V, src, dtype, V, H, 0, 0, 0, st);
   }
   if (name == "visual_head.weight") {
     if (!is2(MM, H)) return shape_err();
-    return repack_bf16(e, e->visual_head, MM, src, dtype, MM, H, 0, 0, 0, st);
+    return repack_w<act_t>(e, e->visual_head, MM, src, dtype, MM, H, 0, 0, 0, st);
   }
   if (name == "model.norm.weight") {
     if (!is1(H)) return shape_err();
@@ -413,9 +425,9 @@ extern "C" int blim_load_weight(blim_engine* e, const char* name_c, const void* 
     else if (rest.compare(0, 8, "tvg_mlp.") == 0) { which = 1; rest = rest.substr(8); }
     else { e->weights_loaded--; return 2; }
     ProjW& p = e->proj[which];
-    if (rest == "0.weight") { if (!is2(H, MM)) return shape_err(); return repack_bf16(e, p.w0, H, src, dtype, H, MM, 0, 0, 0, st); }
+    if (rest == "0.weight") { if (!is2(H, MM)) return shape_err(); return repack_w<act_t>(e, p.w0, H, src, dtype, H, MM, 0, 0, 0, st); }
     if (rest == "0.bias") { if (!is1(H)) return shape_err(); return repack_f32(e, p.b0, H, 0, src, dtype, H, 1, st); }
-    if (rest == "2.weight") { if (!is2(H, H)) return shape_err(); return repack_bf16(e, p.w2, H, src, dtype, H, H, 0, 0, 0, st); }
+    if (rest == "2.weight") { if (!is2(H, H)) return shape_err(); return repack_w<act_t>(e, p.w2, H, src, dtype, H, H, 0, 0, 0, st); }
     if (rest == "2.bias") { if (!is1(H)) return shape_err(); return repack_f32(e, p.b2, H, 0, src, dtype, H, 1, st); }
     e->weights_loaded--;
     return 2;
@@ -432,16 +444,16 @@ extern "C" int blim_load_weight(blim_engine* e, const char* name_c, const void* 
                      rest.find("v_proj.weight") != std::string::npos || rest.find("gate_proj") != std::string::npos ||
                      rest.find("up_proj") != std::string::npos || rest.find("layernorm") != std::string::npos))
       return e->fail("layer " + std::to_string(li) + " is already finalised (norm weights folded into its GEMM weights): create a new engine to reload " + name);
-    if (rest == "self_attn.q_proj.weight") { if (!is2(NQ, H)) return shape_err(); w.loaded |= kLdQ; return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NQ, H, 0, 0, 0, st); }
-    if (rest == "self_attn.k_proj.weight") { if (!is2(NKVD, H)) return shape_err(); w.loaded |= kLdK; return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NKVD, H, NQ, 0, 0, st); }
-    if (rest == "self_attn.v_proj.weight") { if (!is2(NKVD, H)) return shape_err(); w.loaded |= kLdV; return repack_bf16(e, w.w_qkv, NQKV, src, dtype, NKVD, H, NQ + NKVD, 0, 0, st); }
+    if (rest == "self_attn.q_proj.weight") { if (!is2(NQ, H)) return shape_err(); w.loaded |= kLdQ; return repack_w<act_t>(e, w.w_qkv, NQKV, src, dtype, NQ, H, 0, 0, 0, st); }
+    if (rest == "self_attn.k_proj.weight") { if (!is2(NKVD, H)) return shape_err(); w.loaded |= kLdK; return repack_w<act_t>(e, w.w_qkv, NQKV, src, dtype, NKVD, H, NQ, 0, 0, st); }
+    if (rest == "self_attn.v_proj.weight") { if (!is2(NKVD, H)) return shape_err(); w.loaded |= kLdV; return repack_w<act_t>(e, w.w_qkv, NQKV, src, dtype, NKVD, H, NQ + NKVD, 0, 0, st); }
     if (rest == "self_attn.q_proj.bias") { if (!is1(NQ)) return shape_err(); w.loaded |= kLdQb; return repack_f32(e, w.b_qkv, NQKV, 0, src, dtype, NQ, 1, st); }
     if (rest == "self_attn.k_proj.bias") { if (!is1(NKVD)) return shape_err(); w.loaded |= kLdKb; return repack_f32(e, w.b_qkv, NQKV, NQ, src, dtype, NKVD, 1, st); }
     if (rest == "self_attn.v_proj.bias") { if (!is1(NKVD)) return shape_err(); w.loaded |= kLdVb; return repack_f32(e, w.b_qkv, NQKV, NQ + NKVD, src, dtype, NKVD, 1, st); }
-    if (rest == "self_attn.o_proj.weight") { if (!is2(H, NQ)) return shape_err(); w.loaded |= kLdO; return repack_bf16(e, w.w_o, H, src, dtype, H, NQ, 0, 0, 0, st); }
-    if (rest == "mlp.gate_proj.weight") { if (!is2(I, H)) return shape_err(); w.loaded |= kLdGate; return repack_bf16(e, w.w_gu, 2 * static_cast<size_t>(I), src, dtype, I, H, 0, 128, 0, st); }
-    if (rest == "mlp.up_proj.weight") { if (!is2(I, H)) return shape_err(); w.loaded |= kLdUp; return repack_bf16(e, w.w_gu, 2 * static_cast<size_t>(I), src, dtype, I, H, 0, 128, 1, st); }
-    if (rest == "mlp.down_proj.weight") { if (!is2(H, I)) return shape_err(); w.loaded |= kLdDown; return repack_bf16(e, w.w_down, H, src, dtype, H, I, 0, 0, 0, st); }
+    if (rest == "self_attn.o_proj.weight") { if (!is2(H, NQ)) return shape_err(); w.loaded |= kLdO; return repack_w<act_t>(e, w.w_o, H, src, dtype, H, NQ, 0, 0, 0, st); }
+    if (rest == "mlp.gate_proj.weight") { if (!is2(I, H)) return shape_err(); w.loaded |= kLdGate; return repack_w<act_t>(e, w.w_gu, 2 * static_cast<size_t>(I), src, dtype, I, H, 0, 128, 0, st); }
+    if (rest == "mlp.up_proj.weight") { if (!is2(I, H)) return shape_err(); w.loaded |= kLdUp; return repack_w<act_t>(e, w.w_gu, 2 * static_cast<size_t>(I), src, dtype, I, H, 0, 128, 1, st); }
+    if (rest == "mlp.down_proj.weight") { if (!is2(H, I)) return shape_err(); w.loaded |= kLdDown; return repack_w<act_t>(e, w.w_down, H, src, dtype, H, I, 0, 0, 0, st); }
     if (rest == "input_layernorm.weight") { if (!is1(H)) return shape_err(); w.loaded |= kLdLn1; return repack_f32(e, w.ln1, H, 0, src, dtype, H, 1, st); }
     if (rest == "post_attention_layernorm.weight") { if (!is1(H)) return shape_err(); w.loaded |= kLdLn2; return repack_f32(e, w.ln2, H, 0, src, dtype, H, 1, st); }
   }
@@ -471,7 +483,7 @@ extern "C" int blim_set_videos(blim_engine* e, const void* feats_dev, int dtype,
   if (!e || !feats_dev || n_videos <= 0 || n_clips <= 0) return e ? e->fail("bad video arguments") : 1;
   CKE(cudaSetDevice(e->device));
   const int rows = n_videos * n_clips * e->TPC;
-  CKR(repack_bf16(e, e->feats, rows, feats_dev, dtype, rows, e->MM, 0, 0, 0, S(stream)));
+  CKR(repack_act(e, e->feats, rows, feats_dev, dtype, rows, e->MM, S(stream)));
   e->n_videos = n_videos;
   e->n_clips = n_clips;
   e->tvg_vis_ready = false;
@@ -539,7 +551,7 @@ extern "C" int blim_set_video_vocab(blim_engine* e, const void* vocab_dev, int d
   const size_t n = static_cast<size_t>(n_vocab) * e->n_clips * e->MM;
   CKE(e->vocab.reserve(n * 2));
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
-  repack_vocab_kernel<<<blocks, 256, 0, S(stream)>>>(e->vocab.as<bf16>(), vocab_dev, dtype, n_vocab, e->n_clips, e->MM);
+  repack_vocab_kernel<<<blocks, 256, 0, S(stream)>>>(e->vocab.as<act_t>(), vocab_dev, dtype, n_vocab, e->n_clips, e->MM);
   CKL();
   e->n_vocab = n_vocab;
   e->video_labels.assign(labels, labels + n_videos);
@@ -560,7 +572,7 @@ extern "C" int blim_build_video_vocab(blim_engine* e, const int32_t* labels, int
   CKE(e->vocab.reserve(n * 2));
   CKE(cudaMemsetAsync(e->vocab.p, 0, n * 2, st));
   CKR(upload(e, e->d_map, labels, static_cast<size_t>(n_videos) * sizeof(int), st));
-  vocab_from_feats_kernel<<<n_videos * e->n_clips, 128, 0, st>>>(e->vocab.as<bf16>(), e->feats.as<bf16>(), e->d_map.as<int>(), e->n_clips, e->TPC,
+  vocab_from_feats_kernel<<<n_videos * e->n_clips, 128, 0, st>>>(e->vocab.as<act_t>(), e->feats.as<act_t>(), e->d_map.as<int>(), e->n_clips, e->TPC,
                                                                  e->MM, n_vocab);
   CKL();
   e->n_vocab = n_vocab;
@@ -591,8 +603,8 @@ static int check_ready(blim_engine* e, cudaStream_t st) {
     for (int l = 0; l < e->NL; ++l) {
       LayerW& w = e->layers[l];
       if (w.folded) continue;
-      fold_norm_weight_kernel<<<2048, 256, 0, st>>>(w.w_qkv.as<bf16>(), w.ln1.as<float>(), static_cast<size_t>(e->NQKV), e->H);
-      fold_norm_weight_kernel<<<2048, 256, 0, st>>>(w.w_gu.as<bf16>(), w.ln2.as<float>(), 2 * static_cast<size_t>(e->I), e->H);
+      fold_norm_weight_kernel<<<2048, 256, 0, st>>>(w.w_qkv.as<act_t>(), w.ln1.as<float>(), static_cast<size_t>(e->NQKV), e->H);
+      fold_norm_weight_kernel<<<2048, 256, 0, st>>>(w.w_gu.as<act_t>(), w.ln2.as<float>(), 2 * static_cast<size_t>(e->I), e->H);
       w.folded = true;
     }
   }
@@ -633,7 +645,7 @@ static int upload(blim_engine* e, DevBuf& dst, const void* src, size_t bytes, cu
   return 0;
 }
 
-static int rmsnorm(blim_engine* e, bf16* out, const float* x0, const float* x1, const int* idx, const float* w, int R, cudaStream_t st) {
+static int rmsnorm(blim_engine* e, act_t* out, const float* x0, const float* x1, const int* idx, const float* w, int R, cudaStream_t st) {
   if (R <= 0) return 0;
   e->tic(2, st);
   rmsnorm_kernel<<<R, 256, 0, st>>>(out, x0, x1, idx, w, R, e->H, e->cfg.rms_norm_eps);
@@ -643,15 +655,15 @@ static int rmsnorm(blim_engine* e, bf16* out, const float* x0, const float* x1, 
 }
 
 // Projector MLP over `rows` feature rows: Linear -> GELU -> Linear (mm_projector_builder.py:156-159).
-static int project(blim_engine* e, const bf16* feats, int rows, int which, bf16* out, cudaStream_t st) {
+static int project(blim_engine* e, const act_t* feats, int rows, int which, act_t* out, cudaStream_t st) {
   const ProjW& p = e->proj[which];
   if (!p.w0.p || !p.b0.p || !p.w2.p || !p.b2.p) return e->fail(which ? "tvg_mlp weights not loaded" : "mm_projector.mlp weights not loaded");
   for (int r0 = 0; r0 < rows; r0 += e->Tmax) {
     const int n = std::min(e->Tmax, rows - r0);
-    EpiStore<bf16, true, true>::Params p1{e->proj_tmp.as<bf16>(), e->H, p.b0.as<float>()};
-    CKR((gemm<EpiStore<bf16, true, true>>(e, feats + static_cast<size_t>(r0) * e->MM, e->MM, p.w0.as<bf16>(), e->MM, n, e->H, e->MM, p1, st)));
-    EpiStore<bf16, true, false>::Params p2{out + static_cast<size_t>(r0) * e->H, e->H, p.b2.as<float>()};
-    CKR((gemm<EpiStore<bf16, true, false>>(e, e->proj_tmp.as<bf16>(), e->H, p.w2.as<bf16>(), e->H, n, e->H, e->H, p2, st)));
+    EpiStore<act_t, true, true>::Params p1{e->proj_tmp.as<act_t>(), e->H, p.b0.as<float>()};
+    CKR((gemm<EpiStore<act_t, true, true>>(e, feats + static_cast<size_t>(r0) * e->MM, e->MM, p.w0.as<act_t>(), e->MM, n, e->H, e->MM, p1, st)));
+    EpiStore<act_t, true, false>::Params p2{out + static_cast<size_t>(r0) * e->H, e->H, p.b2.as<float>()};
+    CKR((gemm<EpiStore<act_t, true, false>>(e, e->proj_tmp.as<act_t>(), e->H, p.w2.as<act_t>(), e->H, n, e->H, e->H, p2, st)));
   }
   return 0;
 }
@@ -668,21 +680,12 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
   if (to_prefix_cache && T > e->Pmax) return e->fail("internal: prefix run exceeds max_prefix_tokens");
   for (int p : run.tok_pos)
     if (p < 0 || p >= e->rope_n) return e->fail("sequence longer than the rotary table (max_positions)");
-  std::vector<AttnWork> works;
   std::vector<AttnWorkTc> works_tc;
   std::vector<int> seq_start;
-  int n_works;
-  if (e->attn_tc) {
-    build_attn_works_tc(run.seqs.data(), static_cast<int>(run.seqs.size()), e->G, works_tc, seq_start, T);
-    n_works = static_cast<int>(works_tc.size());
-    CKR(upload(e, e->d_works, works_tc.data(), works_tc.size() * sizeof(AttnWorkTc), st));
-    CKR(upload(e, e->d_seq_start, seq_start.data(), T * sizeof(int), st));
-  } else {
-    build_attn_works(run.seqs.data(), static_cast<int>(run.seqs.size()), e->G, works);
-    n_works = static_cast<int>(works.size());
-    CKR(upload(e, e->d_works, works.data(), works.size() * sizeof(AttnWork), st));
-    CKR(upload(e, e->d_seqs, run.seqs.data(), run.seqs.size() * sizeof(AttnSeq), st));
-  }
+  build_attn_works_tc(run.seqs.data(), static_cast<int>(run.seqs.size()), e->G, works_tc, seq_start, T);
+  const int n_works = static_cast<int>(works_tc.size());
+  CKR(upload(e, e->d_works, works_tc.data(), works_tc.size() * sizeof(AttnWorkTc), st));
+  CKR(upload(e, e->d_seq_start, seq_start.data(), T * sizeof(int), st));
   CKR(upload(e, e->d_tok_pos, run.tok_pos.data(), T * sizeof(int), st));
   if (run.any_slot) {
     if (!to_prefix_cache) return e->fail("internal: K/V slots are only remapped in prefix runs");
@@ -694,7 +697,7 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
   if (run.any_invalid) CKR(upload(e, e->d_key_valid, run.key_valid.data(), T, st));
   if (!assembled) {
     CKR(upload(e, e->d_tok_src, run.tok_src.data(), T * sizeof(int), st));
-    assemble_tokens_kernel<<<T, 128, 0, st>>>(e->x.as<float>(), e->embed.as<bf16>(), e->vis.as<bf16>(), e->d_tok_src.as<int>(), T, e->H);
+    assemble_tokens_kernel<<<T, 128, 0, st>>>(e->x.as<float>(), e->embed.as<bf16>(), e->vis.as<act_t>(), e->d_tok_src.as<int>(), T, e->H);
     CKL();
   }
   const size_t kv_layer = static_cast<size_t>(e->Pmax) * e->NKVD;
@@ -702,13 +705,13 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
   const int n_parts = 2 * ((e->H + kBN - 1) / kBN);
   const float* rstd = fuse ? e->rstd.as<float>() : nullptr;
   auto rowprep = [&](const float* x, int R) -> int {   // xn = bf16(x), rstd = 1/rms(x)
-    rowprep_kernel<<<R, 256, 0, st>>>(e->xn.as<bf16>(), e->rstd.as<float>(), x, R, e->H, e->cfg.rms_norm_eps);
+    rowprep_kernel<<<R, 256, 0, st>>>(e->xn.as<act_t>(), e->rstd.as<float>(), x, R, e->H, e->cfg.rms_norm_eps);
     CKL();
     return 0;
   };
-  auto resid_gemm = [&](const bf16* A, int lda, const bf16* W, int K, float* x, int R, bool want_norm) -> int {
+  auto resid_gemm = [&](const act_t* A, int lda, const act_t* W, int K, float* x, int R, bool want_norm) -> int {
     if (want_norm) {   // x += A W^T, xn = bf16(x), rstd = 1/rms(x)  (first half of the next RMSNorm)
-      EpiResidNorm::Params pn{x, e->xn.as<bf16>(), e->ssq.as<float>(), e->H};
+      EpiResidNorm::Params pn{x, e->xn.as<act_t>(), e->ssq.as<float>(), e->H};
       CKR(gemm<EpiResidNorm>(e, A, lda, W, lda, R, e->H, K, pn, st));
       rstd_rows_kernel<<<(R + 255) / 256, 256, 0, st>>>(e->rstd.as<float>(), e->ssq.as<float>(), R, n_parts, e->H, e->cfg.rms_norm_eps);
       CKL();
@@ -720,20 +723,20 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
   if (fuse) CKR(rowprep(e->x.as<float>(), T));
   for (int l = 0; l < e->NL; ++l) {
     const LayerW& w = e->layers[l];
-    bf16* kpl = e->kp.as<bf16>() + l * kv_layer;
-    bf16* vpl = e->vp.as<bf16>() + l * kv_layer;
-    bf16* k_out = to_prefix_cache ? kpl : e->k_own.as<bf16>();
-    bf16* v_out = to_prefix_cache ? vpl : e->v_own.as<bf16>();
-    if (!fuse) CKR(rmsnorm(e, e->xn.as<bf16>(), e->x.as<float>(), nullptr, nullptr, w.ln1.as<float>(), T, st));
-    CKR(gemm_qkv(e, e->xn.as<bf16>(), w, T, e->q.as<bf16>(), k_out, v_out, e->d_tok_pos.as<int>(), kv_slot, rstd, st));
+    act_t* kpl = e->kp.as<act_t>() + l * kv_layer;
+    act_t* vpl = e->vp.as<act_t>() + l * kv_layer;
+    act_t* k_out = to_prefix_cache ? kpl : e->k_own.as<act_t>();
+    act_t* v_out = to_prefix_cache ? vpl : e->v_own.as<act_t>();
+    if (!fuse) CKR(rmsnorm(e, e->xn.as<act_t>(), e->x.as<float>(), nullptr, nullptr, w.ln1.as<float>(), T, st));
+    CKR(gemm_qkv(e, e->xn.as<act_t>(), w, T, e->q.as<act_t>(), k_out, v_out, e->d_tok_pos.as<int>(), kv_slot, rstd, st));
     const bool prune = last_rows != nullptr && l == e->NL - 1;
     if (prune && last_rows->empty()) break;
     const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(e->DH));
     cudaError_t r;
     e->tic(1, st);
-    if (e->attn_tc) {
+    {
       AttnParamsTc ap;
-      ap.q = e->q.as<bf16>(); ap.o = e->attn.as<bf16>();
+      ap.q = e->q.as<act_t>(); ap.o = e->attn.as<act_t>();
       ap.a_row0 = l * e->Pmax;
       ap.b_row0 = to_prefix_cache ? l * e->Pmax : 0;
       AttnTcMaps maps;
@@ -743,15 +746,7 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
       ap.key_valid = run.any_invalid ? e->d_key_valid.as<uint8_t>() : nullptr;
       ap.tok_seq_start = e->d_seq_start.as<int>(); ap.works = e->d_works.as<AttnWorkTc>();
       ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G; ap.scale_log2 = scale_log2; ap.q_stride = e->NQ; ap.n_works = n_works; ap.n_kv_heads = e->NKV;
-      r = launch_attention_tc(maps, ap, n_works, e->NKV, e->DH, st, e->attn_tc_version);
-    } else {
-      AttnParams ap;
-      ap.q = e->q.as<bf16>(); ap.o = e->attn.as<bf16>();
-      ap.k_a = kpl; ap.v_a = vpl; ap.k_b = k_out; ap.v_b = v_out;
-      ap.key_valid = run.any_invalid ? e->d_key_valid.as<uint8_t>() : nullptr;
-      ap.seqs = e->d_seqs.as<AttnSeq>(); ap.works = e->d_works.as<AttnWork>();
-      ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G; ap.scale_log2 = scale_log2;
-      r = launch_attention(ap, n_works, e->NKV, e->DH, st);
+      r = launch_attention_tc<act_t>(maps, ap, n_works, e->NKV, e->DH, st, e->attn_version);
     }
     e->toc(st);
     if (r != cudaSuccess) return e->fail_cuda("attention launch", r);
@@ -761,35 +756,35 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
       const int U = static_cast<int>(last_rows->size());
       if (U > e->Umax) return e->fail("internal: too many prefix units in one run");
       CKR(upload(e, e->d_idx, last_rows->data(), U * sizeof(int), st));
-      gather_rows_bf16_kernel<<<U, 128, 0, st>>>(e->xn.as<bf16>(), e->attn.as<bf16>(), e->d_idx.as<int>(), U, e->NQ);
+      gather_rows_16_kernel<<<U, 128, 0, st>>>(e->xn.as<act_t>(), e->attn.as<act_t>(), e->d_idx.as<int>(), U, e->NQ);
       CKL();
       gather_rows_f32_kernel<<<U, 256, 0, st>>>(e->prefix_last.as<float>(), e->x.as<float>(), e->d_idx.as<int>(), U, e->H);
       CKL();
-      CKR(resid_gemm(e->xn.as<bf16>(), e->NQ, w.w_o.as<bf16>(), e->NQ, e->prefix_last.as<float>(), U, false));
+      CKR(resid_gemm(e->xn.as<act_t>(), e->NQ, w.w_o.as<act_t>(), e->NQ, e->prefix_last.as<float>(), U, false));
       if (fuse) CKR(rowprep(e->prefix_last.as<float>(), U));
-      else CKR(rmsnorm(e, e->xn.as<bf16>(), e->prefix_last.as<float>(), nullptr, nullptr, w.ln2.as<float>(), U, st));
-      EpiSwiglu::Params psl{e->act.as<bf16>(), e->I, rstd};
-      CKR(gemm<EpiSwiglu>(e, e->xn.as<bf16>(), e->H, w.w_gu.as<bf16>(), e->H, U, 2 * e->I, e->H, psl, st));
-      CKR(resid_gemm(e->act.as<bf16>(), e->I, w.w_down.as<bf16>(), e->I, e->prefix_last.as<float>(), U, false));
+      else CKR(rmsnorm(e, e->xn.as<act_t>(), e->prefix_last.as<float>(), nullptr, nullptr, w.ln2.as<float>(), U, st));
+      EpiSwiglu::Params psl{e->act.as<act_t>(), e->I, rstd};
+      CKR(gemm<EpiSwiglu>(e, e->xn.as<act_t>(), e->H, w.w_gu.as<act_t>(), e->H, U, 2 * e->I, e->H, psl, st));
+      CKR(resid_gemm(e->act.as<act_t>(), e->I, w.w_down.as<act_t>(), e->I, e->prefix_last.as<float>(), U, false));
       break;
     }
-    CKR(resid_gemm(e->attn.as<bf16>(), e->NQ, w.w_o.as<bf16>(), e->NQ, e->x.as<float>(), T, fuse));
-    if (!fuse) CKR(rmsnorm(e, e->xn.as<bf16>(), e->x.as<float>(), nullptr, nullptr, w.ln2.as<float>(), T, st));
-    EpiSwiglu::Params ps{e->act.as<bf16>(), e->I, rstd};
-    CKR(gemm<EpiSwiglu>(e, e->xn.as<bf16>(), e->H, w.w_gu.as<bf16>(), e->H, T, 2 * e->I, e->H, ps, st));
-    CKR(resid_gemm(e->act.as<bf16>(), e->I, w.w_down.as<bf16>(), e->I, e->x.as<float>(), T, fuse && l + 1 < e->NL));
+    CKR(resid_gemm(e->attn.as<act_t>(), e->NQ, w.w_o.as<act_t>(), e->NQ, e->x.as<float>(), T, fuse));
+    if (!fuse) CKR(rmsnorm(e, e->xn.as<act_t>(), e->x.as<float>(), nullptr, nullptr, w.ln2.as<float>(), T, st));
+    EpiSwiglu::Params ps{e->act.as<act_t>(), e->I, rstd};
+    CKR(gemm<EpiSwiglu>(e, e->xn.as<act_t>(), e->H, w.w_gu.as<act_t>(), e->H, T, 2 * e->I, e->H, ps, st));
+    CKR(resid_gemm(e->act.as<act_t>(), e->I, w.w_down.as<act_t>(), e->I, e->x.as<float>(), T, fuse && l + 1 < e->NL));
   }
   return 0;
 }
 
 // logp[r] = log softmax(scale * A[r] · W^T)[target[r]] for R rows, never materialising the logits.
-static int lse_rows(blim_engine* e, const bf16* A, int lda, const bf16* W, int ldw, int R, int N, int K, const int* targets_dev, float scale,
-                    float* logp_dev, cudaStream_t st) {
+static int lse_rows(blim_engine* e, const void* A, int lda, const void* W, int ldw, int R, int N, int K, const int* targets_dev, float scale,
+                    float* logp_dev, cudaStream_t st, int b_fmt = kActFmt, int a_fmt = kActFmt) {
   if (R <= 0) return 0;
   const int n_tiles = (N + kBN - 1) / kBN;
   CKE(e->partial.reserve(static_cast<size_t>(e->Tmax) * 2 * n_tiles * sizeof(float2)));
   EpiLse::Params p{e->partial.as<float2>(), e->tgt_logit.as<float>(), targets_dev, scale};
-  CKR(gemm<EpiLse>(e, A, lda, W, ldw, R, N, K, p, st));
+  CKR(gemm<EpiLse>(e, A, lda, W, ldw, R, N, K, p, st, b_fmt, a_fmt));
   lse_finalize_kernel<<<(R + 7) / 8, 256, 0, st>>>(logp_dev, e->partial.as<float2>(), e->tgt_logit.as<float>(), R, 2 * n_tiles);
   CKL();
   return 0;
@@ -865,8 +860,8 @@ static int ensure_tvg_vis(blim_engine* e, cudaStream_t st) {
   const int clips_per_chunk = std::max(1, std::min(e->Pmax, e->Tmax) / e->TPC);
   for (int c0 = 0; c0 < n_rows; c0 += clips_per_chunk) {
     const int nc = std::min(clips_per_chunk, n_rows - c0);
-    CKR(project(e, e->feats.as<bf16>() + static_cast<size_t>(c0) * e->TPC * e->MM, nc * e->TPC, 1, e->vis.as<bf16>(), st));
-    mean_rows_kernel<<<nc, 256, 0, st>>>(e->tvg_vis.as<bf16>() + static_cast<size_t>(c0) * e->H, e->vis.as<bf16>(), nc, e->TPC, e->H);
+    CKR(project(e, e->feats.as<act_t>() + static_cast<size_t>(c0) * e->TPC * e->MM, nc * e->TPC, 1, e->vis.as<act_t>(), st));
+    mean_rows_kernel<<<nc, 256, 0, st>>>(e->tvg_vis.as<act_t>() + static_cast<size_t>(c0) * e->H, e->vis.as<act_t>(), nc, e->TPC, e->H);
     CKL();
   }
   e->tvg_vis_ready = true;
@@ -889,7 +884,7 @@ static int prefill_root(blim_engine* e, const int32_t* ids, int R, const std::ve
   if (U == 0) return 0;
   CKR(upload(e, e->d_idx, unit_bases.data(), U * sizeof(int), st));
   dim3 grid(static_cast<unsigned>(U), static_cast<unsigned>(e->NL), 2);
-  replicate_root_rows_kernel<<<grid, 128, 0, st>>>(e->kp.as<bf16>(), e->vp.as<bf16>(), e->d_idx.as<int>(), R, e->NKVD,
+  replicate_root_rows_kernel<<<grid, 128, 0, st>>>(e->kp.as<act_t>(), e->vp.as<act_t>(), e->d_idx.as<int>(), R, e->NKVD,
                                                    static_cast<size_t>(e->Pmax) * e->NKVD);
   CKL();
   return 0;
@@ -951,15 +946,15 @@ static int score_vtg(blim_engine* e, bool prior, const std::vector<std::pair<int
       bool contiguous = true;
       for (size_t i = 1; i < by_row.size(); ++i) contiguous = contiguous && by_row[i].second == by_row[i - 1].second + 1;
       if (contiguous) {
-        CKR(project(e, e->feats.as<bf16>() + static_cast<size_t>(by_row[0].second) * n_vis * e->MM, rows, 0, e->vis.as<bf16>(), st));
+        CKR(project(e, e->feats.as<act_t>() + static_cast<size_t>(by_row[0].second) * n_vis * e->MM, rows, 0, e->vis.as<act_t>(), st));
       } else {
         std::vector<int> idx(rows);
         for (const auto& rv : by_row)
           for (int i = 0; i < n_vis; ++i) idx[rv.first + i] = rv.second * n_vis + i;
         CKR(upload(e, e->d_vis_idx, idx.data(), static_cast<size_t>(rows) * 4, st));
-        gather_rows_bf16_kernel<<<rows, 128, 0, st>>>(e->vis_in.as<bf16>(), e->feats.as<bf16>(), e->d_vis_idx.as<int>(), rows, e->MM);
+        gather_rows_16_kernel<<<rows, 128, 0, st>>>(e->vis_in.as<act_t>(), e->feats.as<act_t>(), e->d_vis_idx.as<int>(), rows, e->MM);
         CKL();
-        CKR(project(e, e->vis_in.as<bf16>(), rows, 0, e->vis.as<bf16>(), st));
+        CKR(project(e, e->vis_in.as<act_t>(), rows, 0, e->vis.as<act_t>(), st));
       }
     }
     // ---- prefix run.  With a shared root (all units of the batch use the same prompt group) the header tokens are
@@ -1049,8 +1044,8 @@ static int score_vtg(blim_engine* e, bool prior, const std::vector<std::pair<int
       std::vector<int> off_local(i1 - i0 + 1);
       for (int i = i0; i <= i1; ++i) off_local[i - i0] = row_off[i] - r0;
       CKR(upload(e, e->d_row_off, off_local.data(), off_local.size() * sizeof(int), st));
-      CKR(rmsnorm(e, e->lm_a.as<bf16>(), e->x.as<float>(), e->prefix_last.as<float>(), e->d_idx.as<int>(), e->norm.as<float>(), R, st));
-      CKR(lse_rows(e, e->lm_a.as<bf16>(), e->H, e->lm_head.as<bf16>(), e->H, R, e->V, e->H, e->d_targets.as<int>(), 1.0f, e->logp.as<float>(), st));
+      CKR(rmsnorm(e, e->lm_a.as<act_t>(), e->x.as<float>(), e->prefix_last.as<float>(), e->d_idx.as<int>(), e->norm.as<float>(), R, st));
+      CKR(lse_rows(e, e->lm_a.as<act_t>(), e->H, e->lm_head.as<act_t>(), e->H, R, e->V, e->H, e->d_targets.as<int>(), 1.0f, e->logp.as<float>(), st));
       // item scores land in a staging area (reuse tgt_logit after finalize is done with it: stream ordered)
       const int P = i1 - i0;
       vtg_seq_mean_kernel<<<(P + 7) / 8, 256, 0, st>>>(e->tgt_logit.as<float>(), e->logp.as<float>(), e->d_row_off.as<int>(), P);
@@ -1215,7 +1210,7 @@ static int score_tvg(blim_engine* e, bool prior, const std::vector<std::pair<int
       // assemble with the pooled table as the visual source
       const int T = run.T();
       CKR(upload(e, e->d_tok_src, run.tok_src.data(), T * sizeof(int), st));
-      assemble_tokens_kernel<<<T, 128, 0, st>>>(e->x.as<float>(), e->embed.as<bf16>(), e->tvg_vis.as<bf16>(), e->d_tok_src.as<int>(), T, e->H);
+      assemble_tokens_kernel<<<T, 128, 0, st>>>(e->x.as<float>(), e->embed.as<bf16>(), e->tvg_vis.as<act_t>(), e->d_tok_src.as<int>(), T, e->H);
       CKL();
       CKR(run_decoder(e, run, false, true, st));
     }
@@ -1238,11 +1233,11 @@ static int score_tvg(blim_engine* e, bool prior, const std::vector<std::pair<int
       const int R = NC * P;
       CKR(upload(e, e->d_idx, row_idx.data(), R * sizeof(int), st));
       CKR(upload(e, e->d_targets, targets.data(), P * sizeof(int), st));
-      CKR(rmsnorm(e, e->lm_a.as<bf16>(), e->x.as<float>(), e->prefix_last.as<float>(), e->d_idx.as<int>(), e->norm.as<float>(), R, st));
-      EpiStore<bf16, false, false>::Params pv{e->pred.as<bf16>(), e->MM, nullptr};
-      CKR((gemm<EpiStore<bf16, false, false>>(e, e->lm_a.as<bf16>(), e->H, e->visual_head.as<bf16>(), e->H, R, e->MM, e->H, pv, st)));
+      CKR(rmsnorm(e, e->lm_a.as<act_t>(), e->x.as<float>(), e->prefix_last.as<float>(), e->d_idx.as<int>(), e->norm.as<float>(), R, st));
+      EpiStore<act_t, false, false>::Params pv{e->pred.as<act_t>(), e->MM, nullptr};
+      CKR((gemm<EpiStore<act_t, false, false>>(e, e->lm_a.as<act_t>(), e->H, e->visual_head.as<act_t>(), e->H, R, e->MM, e->H, pv, st)));
       for (int c = 0; c < NC; ++c) {
-        CKR(lse_rows(e, e->pred.as<bf16>() + static_cast<size_t>(c) * P * e->MM, e->MM, e->vocab.as<bf16>() + static_cast<size_t>(c) * e->n_vocab * e->MM,
+        CKR(lse_rows(e, e->pred.as<act_t>() + static_cast<size_t>(c) * P * e->MM, e->MM, e->vocab.as<act_t>() + static_cast<size_t>(c) * e->n_vocab * e->MM,
                      e->MM, P, e->n_vocab, e->MM, e->d_targets.as<int>(), scale, e->logp.as<float>() + static_cast<size_t>(c) * P, st));
       }
       tvg_clip_mean_kernel<<<(P + 255) / 256, 256, 0, st>>>(e->tgt_logit.as<float>(), e->logp.as<float>(), P, NC);
@@ -1322,6 +1317,20 @@ extern "C" int blim_score_pairs(blim_engine* e, int kind, const int32_t* pair_v,
   return 0;
 }
 
+// dst[i] = Dst(src[i]) for 16-bit formats (the compat entry points speak bf16, the engine's activations are act_t)
+template <typename Dst, typename Src>
+__global__ void convert16_kernel(Dst* __restrict__ dst, const Src* __restrict__ src, size_t n) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = Fmt16<Dst>::from_float(Fmt16<Src>::to_float(src[i]));
+}
+template <typename Dst, typename Src>
+static int convert16(blim_engine* e, Dst* dst, const Src* src, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  convert16_kernel<Dst, Src><<<static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, st>>>(dst, src, n);
+  CKL();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ compat forward
 extern "C" int blim_forward_logits(blim_engine* e, const void* embeds, const int32_t* mask_dev, int B, int L, float* logits, void* hidden,
                                    void* stream) {
@@ -1353,12 +1362,11 @@ extern "C" int blim_forward_logits(blim_engine* e, const void* embeds, const int
         e->x.as<float>(), reinterpret_cast<const bf16*>(embeds) + static_cast<size_t>(b0) * L * e->H, n);
     CKL();
     CKR(run_decoder(e, run, false, true, st));
-    CKR(rmsnorm(e, e->lm_a.as<bf16>(), e->x.as<float>(), nullptr, nullptr, e->norm.as<float>(), T, st));
-    if (hidden)
-      CKE(cudaMemcpyAsync(reinterpret_cast<bf16*>(hidden) + static_cast<size_t>(b0) * L * e->H, e->lm_a.p, n * 2, cudaMemcpyDeviceToDevice, st));
+    CKR(rmsnorm(e, e->lm_a.as<act_t>(), e->x.as<float>(), nullptr, nullptr, e->norm.as<float>(), T, st));
+    if (hidden) CKR(convert16(e, reinterpret_cast<bf16*>(hidden) + static_cast<size_t>(b0) * L * e->H, e->lm_a.as<act_t>(), n, st));
     if (logits) {
       EpiStore<float, false, false>::Params p{logits + static_cast<size_t>(b0) * L * e->V, e->V, nullptr};
-      CKR((gemm<EpiStore<float, false, false>>(e, e->lm_a.as<bf16>(), e->H, e->lm_head.as<bf16>(), e->H, T, e->V, e->H, p, st)));
+      CKR((gemm<EpiStore<float, false, false>>(e, e->lm_a.as<act_t>(), e->H, e->lm_head.as<act_t>(), e->H, T, e->V, e->H, p, st)));
     }
   }
   return 0;
@@ -1368,7 +1376,12 @@ extern "C" int blim_project_video(blim_engine* e, const void* feats, int n_rows,
   if (!e) return 1;
   if (!feats || !out || n_rows < 0) return e->fail("bad projector arguments");
   CKE(cudaSetDevice(e->device));
-  return project(e, reinterpret_cast<const bf16*>(feats), n_rows, tvg ? 1 : 0, reinterpret_cast<bf16*>(out), S(stream));
+  cudaStream_t st = S(stream);
+  CKE(e->io_in.reserve(static_cast<size_t>(n_rows) * e->MM * 2));
+  CKE(e->io_out.reserve(static_cast<size_t>(n_rows) * e->H * 2));
+  CKR(convert16(e, e->io_in.as<act_t>(), reinterpret_cast<const bf16*>(feats), static_cast<size_t>(n_rows) * e->MM, st));
+  CKR(project(e, e->io_in.as<act_t>(), n_rows, tvg ? 1 : 0, e->io_out.as<act_t>(), st));
+  return convert16(e, reinterpret_cast<bf16*>(out), e->io_out.as<act_t>(), static_cast<size_t>(n_rows) * e->H, st);
 }
 
 extern "C" int blim_forward_visual(blim_engine* e, const void* hidden, int n_rows, void* out, void* stream) {
@@ -1376,9 +1389,13 @@ extern "C" int blim_forward_visual(blim_engine* e, const void* hidden, int n_row
   if (!hidden || !out || n_rows < 0) return e->fail("bad forward_visual arguments");
   if (!e->visual_head.p) return e->fail("visual_head weight not loaded");
   CKE(cudaSetDevice(e->device));
-  EpiStore<bf16, false, false>::Params p{reinterpret_cast<bf16*>(out), e->MM, nullptr};
-  return gemm<EpiStore<bf16, false, false>>(e, reinterpret_cast<const bf16*>(hidden), e->H, e->visual_head.as<bf16>(), e->H, n_rows, e->MM, e->H, p,
-                                            S(stream));
+  cudaStream_t st = S(stream);
+  CKE(e->io_in.reserve(static_cast<size_t>(n_rows) * e->H * 2));
+  CKE(e->io_out.reserve(static_cast<size_t>(n_rows) * e->MM * 2));
+  CKR(convert16(e, e->io_in.as<act_t>(), reinterpret_cast<const bf16*>(hidden), static_cast<size_t>(n_rows) * e->H, st));
+  EpiStore<act_t, false, false>::Params p{e->io_out.as<act_t>(), e->MM, nullptr};
+  CKR((gemm<EpiStore<act_t, false, false>>(e, e->io_in.as<act_t>(), e->H, e->visual_head.as<act_t>(), e->H, n_rows, e->MM, e->H, p, st)));
+  return convert16(e, reinterpret_cast<bf16*>(out), e->io_out.as<act_t>(), static_cast<size_t>(n_rows) * e->MM, st);
 }
 
 __global__ void embed_rows_kernel(bf16* __restrict__ out, const bf16* __restrict__ embed, const int* __restrict__ ids, int n, int H) {
@@ -1520,6 +1537,8 @@ extern "C" int blim_profile_read_detail(blim_engine* e, int n, double* ms, doubl
   return 0;
 }
 
+// 1 = bf16, 2 = fp16 (same codes as blim_load_weight's dtype): the 16-bit format of the engine's activation operands
+extern "C" int blim_act_dtype(void) { return kActFmt == kFmtF16 ? 2 : 1; }
 extern "C" int64_t blim_kernel_launches(const blim_engine* e) { return e ? e->launches + e->gemm.launches : 0; }
 extern "C" double blim_gemm_flops(const blim_engine* e) { return e ? e->flops : 0.0; }
 
@@ -1532,17 +1551,17 @@ extern "C" int blim_debug_gemm(blim_engine* e, int epilogue, const void* A, cons
   cudaStream_t st = S(stream);
   const int saved = e->gemm.cta_group;
   if (cta_group == 1 || cta_group == 2) e->gemm.cta_group = cta_group;
-  const bf16* a = reinterpret_cast<const bf16*>(A);
-  const bf16* w = reinterpret_cast<const bf16*>(W);
+  const act_t* a = reinterpret_cast<const act_t*>(A);   // operand format (blim_act_dtype), like every GEMM operand of the path
+  const act_t* w = reinterpret_cast<const act_t*>(W);
   int r = 0;
   switch (epilogue) {
-    case 0: { EpiStore<bf16, false, false>::Params p{reinterpret_cast<bf16*>(C), N, nullptr}; r = gemm<EpiStore<bf16, false, false>>(e, a, K, w, K, M, N, K, p, st); break; }
-    case 1: { EpiStore<bf16, true, false>::Params p{reinterpret_cast<bf16*>(C), N, bias}; r = gemm<EpiStore<bf16, true, false>>(e, a, K, w, K, M, N, K, p, st); break; }
-    case 2: { EpiStore<bf16, true, true>::Params p{reinterpret_cast<bf16*>(C), N, bias}; r = gemm<EpiStore<bf16, true, true>>(e, a, K, w, K, M, N, K, p, st); break; }
+    case 0: { EpiStore<act_t, false, false>::Params p{reinterpret_cast<act_t*>(C), N, nullptr}; r = gemm<EpiStore<act_t, false, false>>(e, a, K, w, K, M, N, K, p, st); break; }
+    case 1: { EpiStore<act_t, true, false>::Params p{reinterpret_cast<act_t*>(C), N, bias}; r = gemm<EpiStore<act_t, true, false>>(e, a, K, w, K, M, N, K, p, st); break; }
+    case 2: { EpiStore<act_t, true, true>::Params p{reinterpret_cast<act_t*>(C), N, bias}; r = gemm<EpiStore<act_t, true, true>>(e, a, K, w, K, M, N, K, p, st); break; }
     case 3: { EpiStore<float, false, false>::Params p{reinterpret_cast<float*>(C), N, nullptr}; r = gemm<EpiStore<float, false, false>>(e, a, K, w, K, M, N, K, p, st); break; }
     case 4: { EpiResid::Params p{reinterpret_cast<float*>(C), N}; r = gemm<EpiResid>(e, a, K, w, K, M, N, K, p, st); break; }
     case 7: { EpiResidT<1>::Params p{reinterpret_cast<float*>(C), N}; r = gemm<EpiResidT<1>>(e, a, K, w, K, M, N, K, p, st); break; }
-    case 5: { EpiSwiglu::Params p{reinterpret_cast<bf16*>(C), N / 2, nullptr}; r = gemm<EpiSwiglu>(e, a, K, w, K, M, N, K, p, st); break; }
+    case 5: { EpiSwiglu::Params p{reinterpret_cast<act_t*>(C), N / 2, nullptr}; r = gemm<EpiSwiglu>(e, a, K, w, K, M, N, K, p, st); break; }
     case 6: {
       if (M > e->Tmax) { r = e->fail("debug_gemm lse: M exceeds max_run_tokens"); break; }
       r = lse_rows(e, a, K, w, K, M, N, K, target, scale, reinterpret_cast<float*>(C), st);

@@ -21,6 +21,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "act_type.cuh"
 #include "ptx_sm100.cuh"
 
 namespace blim {
@@ -50,6 +51,7 @@ struct GemmDims {
   int n_tiles;   // number of kBN-column tiles
   int sb_tiles;  // m-tiles per super-block (L2 blocking of the A operand)
   int l2_hints;  // 1: A (the super-block slab, reused by every n-tile) is loaded evict_last, W (streamed once per super-block) evict_first
+  int a_fmt, b_fmt;  // 16-bit formats of the operands (kFmtF16 / kFmtBF16), independent of each other (act_type.cuh)
 };
 
 // tile t -> (m_tile, n_tile): super-blocks of sb_tiles m-tiles; inside a super-block m runs fastest so the CTAs that run
@@ -65,28 +67,25 @@ __device__ __forceinline__ void tile_coords(const GemmDims& d, int t, int& m_til
 }
 
 // ------------------------------------------------------------------------------------------------ epilogue helpers
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// Store 32 consecutive bf16 of one row (this thread's row).  `valid` = number of in-range columns (<= 32).
-__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float (&v)[32], int valid) {
+// Store 32 consecutive 16-bit values (T = __nv_bfloat16 or __half) of one row (this thread's row).  `valid` = number of
+// in-range columns (<= 32).
+template <typename T>
+__device__ __forceinline__ void store_row32_16(T* dst, const float (&v)[32], int valid) {
   if (valid >= 32) {
     uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint4 u;
-      u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-      u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-      u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      u.x = Fmt16<T>::pack2(v[8 * i + 0], v[8 * i + 1]);
+      u.y = Fmt16<T>::pack2(v[8 * i + 2], v[8 * i + 3]);
+      u.z = Fmt16<T>::pack2(v[8 * i + 4], v[8 * i + 5]);
+      u.w = Fmt16<T>::pack2(v[8 * i + 6], v[8 * i + 7]);
       d4[i] = u;
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-      if (i < valid) dst[i] = __float2bfloat16(v[i]);
+      if (i < valid) dst[i] = Fmt16<T>::from_float(v[i]);
   }
 }
 __device__ __forceinline__ void store_row32_f32(float* dst, const float (&v)[32], int valid) {
@@ -127,14 +126,15 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // out[row, col .. col+31] = bf16(v) for the 32 rows of a warp (lane = row).  Row-per-thread stores scatter every warp
 // instruction over 32 rows (32 half-used sectors); the warp's 32 x 64 B go through its shared-memory slab instead and
 // are stored 8 rows x 64 contiguous bytes per instruction.  r0 = first row of the warp.
-__device__ __forceinline__ void store_tile32_bf16_staged(__nv_bfloat16* __restrict__ out, int ldo, int r0, int col, const float (&v)[32], int M,
-                                                         uint8_t* wstage) {
+template <typename T>
+__device__ __forceinline__ void store_tile32_16_staged(T* __restrict__ out, int ldo, int r0, int col, const float (&v)[32], int M,
+                                                       uint8_t* wstage) {
   const int lane = threadIdx.x & 31;
   uint4* srow = reinterpret_cast<uint4*>(wstage + lane * 80);
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-    srow[i] = make_uint4(pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                         pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+    srow[i] = make_uint4(Fmt16<T>::pack2(v[8 * i + 0], v[8 * i + 1]), Fmt16<T>::pack2(v[8 * i + 2], v[8 * i + 3]),
+                         Fmt16<T>::pack2(v[8 * i + 4], v[8 * i + 5]), Fmt16<T>::pack2(v[8 * i + 6], v[8 * i + 7]));
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -149,7 +149,7 @@ __device__ __forceinline__ void store_tile32_bf16_staged(__nv_bfloat16* __restri
 // only the global-memory side is predicated), the tile's first column n0, the TMEM address of (its lane, column 0
 // of the accumulator stage) and `half` (0/1): which half of the tile's work this epilogue warpgroup owns.
 
-// out[row, col] = act(acc + bias[col])   OutT = __nv_bfloat16 or float
+// out[row, col] = act(acc + bias[col])   OutT = __nv_bfloat16, __half or float
 template <typename OutT, bool kBias, bool kGelu>
 struct EpiStore {
   static constexpr int kGroups = 2;
@@ -187,9 +187,9 @@ struct EpiStore {
       }
       if constexpr (sizeof(OutT) == 2) {
         if (valid >= 32) {   // warp-uniform
-          store_tile32_bf16_staged(reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, row - static_cast<int>(threadIdx.x & 31), col, v, d.M, wstage);
+          store_tile32_16_staged<OutT>(p.out, p.ldo, row - static_cast<int>(threadIdx.x & 31), col, v, d.M, wstage);
         } else if (row_ok) {
-          store_row32_bf16(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col, v, valid);
+          store_row32_16<OutT>(p.out + static_cast<size_t>(row) * p.ldo + col, v, valid);
         }
       } else if (row_ok) {
         store_row32_f32(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col, v, valid);
@@ -299,7 +299,7 @@ struct EpiResidNorm {
   static constexpr int kGroups = 2;
   struct Params {
     float* resid;          // [M, N] in / out
-    __nv_bfloat16* xb;     // [M, N] out
+    act_t* xb;             // [M, N] out
     float* ssq;            // [M, 2 * n_tiles] out
     int ldo;
   };
@@ -331,7 +331,7 @@ struct EpiResidNorm {
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) ss = fmaf(v[i], v[i], ss);
-        store_row32_bf16(p.xb + static_cast<size_t>(row) * p.ldo + col, v, valid);
+        store_row32_16<act_t>(p.xb + static_cast<size_t>(row) * p.ldo + col, v, valid);
       }
     }
     if (row_ok) p.ssq[static_cast<size_t>(row) * (2 * d.n_tiles) + 2 * n_tile + half] = ss;
@@ -349,9 +349,9 @@ template <int kHeadDim>
 struct EpiQkvRope {
   static constexpr int kGroups = 2;
   struct Params {
-    __nv_bfloat16* q_out;  // [M, n_q]
-    __nv_bfloat16* k_out;  // [slots, n_kv]
-    __nv_bfloat16* v_out;  // [slots, n_kv]
+    act_t* q_out;  // [M, n_q]
+    act_t* k_out;  // [slots, n_kv]
+    act_t* v_out;  // [slots, n_kv]
     const float* bias;     // [n_q + 2 n_kv]
     const int* pos;        // [M] rotary position of each token
     const int* kv_slot;    // [M] cache row of each token (nullptr: row index)
@@ -384,7 +384,7 @@ struct EpiQkvRope {
       const int h = head0 + hh;
       const int c0 = n0 + h * kHeadDim;  // first fused column of this head
       if (c0 >= d.N) break;              // warp-uniform
-      __nv_bfloat16* dst;
+      act_t* dst;
       bool rope;
       if (c0 < p.n_q) {
         dst = p.q_out + static_cast<size_t>(row) * p.n_q + c0;
@@ -408,8 +408,8 @@ struct EpiQkvRope {
         hi[i] = rope ? b * cs[i] + a * sn[i] : b;
       }
       if (row_ok) {
-        store_row32_bf16(dst + j0, lo, 32);
-        store_row32_bf16(dst + kHalf + j0, hi, 32);
+        store_row32_16<act_t>(dst + j0, lo, 32);
+        store_row32_16<act_t>(dst + kHalf + j0, hi, 32);
       }
     }
   }
@@ -420,7 +420,7 @@ struct EpiQkvRope {
 struct EpiSwiglu {
   static constexpr int kGroups = 2;
   struct Params {
-    __nv_bfloat16* act;  // [M, I]
+    act_t* act;          // [M, I]
     int ldo;             // = I
     const float* rstd;   // [M] 1/rms of the (un-normalised) A rows, nullptr = A is already normalised
   };
@@ -441,7 +441,7 @@ struct EpiSwiglu {
         g[i] = x * fast_rcp(1.0f + fast_exp2(-1.4426950408889634f * x)) * (u[i] * rs);   // silu(x) * up: one MUFU.EX2 + one MUFU.RCP
 #endif
       }
-      store_tile32_bf16_staged(p.act, p.ldo, row - static_cast<int>(threadIdx.x & 31), n_tile * 128 + c, g, d.M, wstage);
+      store_tile32_16_staged<act_t>(p.act, p.ldo, row - static_cast<int>(threadIdx.x & 31), n_tile * 128 + c, g, d.M, wstage);
     }
   }
 };
@@ -581,7 +581,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
   } else if (warp == 1 && lane == 0 && is_leader) {
     // ===================================================== MMA issuer (single thread)
-    constexpr uint32_t idesc = make_idesc_bf16(kBM * kCtaGroup, kBN);
+    const uint32_t idesc = make_idesc_f16kind(kBM * kCtaGroup, kBN, dims.a_fmt, dims.b_fmt);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -652,6 +652,7 @@ inline PFN_encodeTiled get_encode_fn() {
 }
 
 // bf16 row-major [rows, cols] matrix, row pitch ld elements; box = 64 columns x box_rows rows, 128 B swizzle.
+// (16-bit elements: the map only moves bytes, so bf16 and fp16 tensors use the same encoding)
 inline bool make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return false;
@@ -677,8 +678,8 @@ struct GemmLaunchCtx {
 };
 
 template <class Epi, int kCtaGroup>
-inline cudaError_t launch_gemm_impl(GemmLaunchCtx& ctx, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N,
-                                    int K, const typename Epi::Params& ep, cudaStream_t stream) {
+inline cudaError_t launch_gemm_impl(GemmLaunchCtx& ctx, const void* A, int lda, const void* W, int ldw, int M, int N,
+                                    int K, const typename Epi::Params& ep, cudaStream_t stream, int a_fmt, int b_fmt) {
   using Cfg = GemmCfg<kCtaGroup>;
   if (M <= 0 || N <= 0) return cudaSuccess;
   if (K <= 0 || (K % kBK) != 0) return cudaErrorInvalidValue;
@@ -708,6 +709,7 @@ inline cudaError_t launch_gemm_impl(GemmLaunchCtx& ctx, const __nv_bfloat16* A, 
   }
   d.sb_tiles = static_cast<int>(sb);
   d.l2_hints = ctx.l2_hints;
+  d.a_fmt = a_fmt; d.b_fmt = b_fmt;
   auto kern = gemm_tcgen05_kernel<Epi, kCtaGroup>;
   static bool attr_set[64] = {};  // per instantiation AND per device (function attributes are per device)
   const int dev_slot = ctx.device & 63;
@@ -732,11 +734,12 @@ inline cudaError_t launch_gemm_impl(GemmLaunchCtx& ctx, const __nv_bfloat16* A, 
   return cudaLaunchKernelEx(&cfg, kern, ta, tb, d, ep);
 }
 
+// A [M, K] and W [N, K] are 16-bit K-major operands in the formats a_fmt / b_fmt (kFmtF16 / kFmtBF16).
 template <class Epi>
-inline cudaError_t launch_gemm(GemmLaunchCtx& ctx, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
-                               const typename Epi::Params& ep, cudaStream_t stream) {
-  if (ctx.cta_group == 2) return launch_gemm_impl<Epi, 2>(ctx, A, lda, W, ldw, M, N, K, ep, stream);
-  return launch_gemm_impl<Epi, 1>(ctx, A, lda, W, ldw, M, N, K, ep, stream);
+inline cudaError_t launch_gemm(GemmLaunchCtx& ctx, const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                               const typename Epi::Params& ep, cudaStream_t stream, int a_fmt = kFmtBF16, int b_fmt = kFmtBF16) {
+  if (ctx.cta_group == 2) return launch_gemm_impl<Epi, 2>(ctx, A, lda, W, ldw, M, N, K, ep, stream, a_fmt, b_fmt);
+  return launch_gemm_impl<Epi, 1>(ctx, A, lda, W, ldw, M, N, K, ep, stream, a_fmt, b_fmt);
 }
 
 }  // namespace blim

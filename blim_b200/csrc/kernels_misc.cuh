@@ -7,30 +7,35 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "act_type.cuh"
+
 namespace blim {
 
 // ------------------------------------------------------------------------------------------------ sequence assembly
 // Replaces embed_tokens + the torch.cat splice of prepare_inputs_labels_for_multimodal (reference:
 // modeling_videochat_flash.py:395-433) without padding: token t takes row tok_src[t] of the embedding table when
 // tok_src[t] >= 0, else row (-1 - tok_src[t]) of the projected visual rows.  Output: fp32 residual stream.
+// The embedding table is a weight (bf16); the visual rows are activations (act_t).
 __global__ void assemble_tokens_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ embed,
-                                       const __nv_bfloat16* __restrict__ visual, const int* __restrict__ tok_src, int T, int H) {
+                                       const act_t* __restrict__ visual, const int* __restrict__ tok_src, int T, int H) {
   const int t = blockIdx.x;
   if (t >= T) return;
   const int src = tok_src[t];
-  const __nv_bfloat16* row = src >= 0 ? embed + static_cast<size_t>(src) * H : visual + static_cast<size_t>(-1 - src) * H;
+  const bool is_tok = src >= 0;
+  const uint16_t* row = is_tok ? reinterpret_cast<const uint16_t*>(embed) + static_cast<size_t>(src) * H
+                               : reinterpret_cast<const uint16_t*>(visual) + static_cast<size_t>(-1 - src) * H;
   float* dst = x + static_cast<size_t>(t) * H;
   for (int c = threadIdx.x * 8; c < H; c += blockDim.x * 8) {
     const uint4 u = *reinterpret_cast<const uint4*>(row + c);
-    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-    float4 lo, hi;
-    float2 f;
-    f = __bfloat1622float2(b2[0]); lo.x = f.x; lo.y = f.y;
-    f = __bfloat1622float2(b2[1]); lo.z = f.x; lo.w = f.y;
-    f = __bfloat1622float2(b2[2]); hi.x = f.x; hi.y = f.y;
-    f = __bfloat1622float2(b2[3]); hi.z = f.x; hi.w = f.y;
-    *reinterpret_cast<float4*>(dst + c) = lo;
-    *reinterpret_cast<float4*>(dst + c + 4) = hi;
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 v = is_tok ? Fmt16<__nv_bfloat16>::unpack2(w[i]) : Fmt16<act_t>::unpack2(w[i]);
+      f[2 * i] = v.x; f[2 * i + 1] = v.y;
+    }
+    *reinterpret_cast<float4*>(dst + c) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(dst + c + 4) = make_float4(f[4], f[5], f[6], f[7]);
   }
 }
 
@@ -47,9 +52,10 @@ __global__ void bf16_rows_to_f32_kernel(float* __restrict__ x, const __nv_bfloat
 
 // ------------------------------------------------------------------------------------------------ RMSNorm
 // Reference: Qwen2RMSNorm.forward (modeling_qwen2_flash.py:93-98): fp32 variance, x * rsqrt(var + eps) cast to the model
-// dtype, then multiplied by the (model dtype) weight.  Both roundings are reproduced.  Row gather: row r reads
+// dtype, then multiplied by the (model dtype) weight.  Here the product is formed in fp32 and rounded ONCE to the
+// activation format (the reference's intermediate cast only adds a rounding).  Row gather: row r reads
 // x0[idx[r]] when idx[r] >= 0 else x1[-1 - idx[r]] (idx == nullptr -> identity on x0).
-__global__ void rmsnorm_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ x0, const float* __restrict__ x1,
+__global__ void rmsnorm_kernel(act_t* __restrict__ out, const float* __restrict__ x0, const float* __restrict__ x1,
                                const int* __restrict__ idx, const float* __restrict__ weight, int R, int H, float eps) {
   const int r = blockIdx.x;
   if (r >= R) return;
@@ -76,18 +82,13 @@ __global__ void rmsnorm_kernel(__nv_bfloat16* __restrict__ out, const float* __r
   }
   __syncthreads();
   const float rstd = rsqrtf(red[0] / static_cast<float>(H) + eps);
-  __nv_bfloat16* dst = out + static_cast<size_t>(r) * H;
+  act_t* dst = out + static_cast<size_t>(r) * H;
   for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
     const float4 v = *reinterpret_cast<const float4*>(src + c);
     const float4 w = *reinterpret_cast<const float4*>(weight + c);
-    const float y0 = __bfloat162float(__float2bfloat16(v.x * rstd)) * w.x;
-    const float y1 = __bfloat162float(__float2bfloat16(v.y * rstd)) * w.y;
-    const float y2 = __bfloat162float(__float2bfloat16(v.z * rstd)) * w.z;
-    const float y3 = __bfloat162float(__float2bfloat16(v.w * rstd)) * w.w;
-    __nv_bfloat162 a = __floats2bfloat162_rn(y0, y1), b = __floats2bfloat162_rn(y2, y3);
     uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&a);
-    u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.x = Fmt16<act_t>::pack2((v.x * rstd) * w.x, (v.y * rstd) * w.y);
+    u.y = Fmt16<act_t>::pack2((v.z * rstd) * w.z, (v.w * rstd) * w.w);
     *reinterpret_cast<uint2*>(dst + c) = u;
   }
 }
@@ -101,8 +102,8 @@ __global__ void rstd_rows_kernel(float* __restrict__ rstd, const float* __restri
   for (int i = 0; i < n_parts; ++i) s += parts[static_cast<size_t>(r) * n_parts + i];
   rstd[r] = rsqrtf(s / static_cast<float>(H) + eps);
 }
-// Entry of a decoder run (and the pruned last layer): xb = bf16(x), rstd = 1/rms(x) for R fp32 rows.
-__global__ void rowprep_kernel(__nv_bfloat16* __restrict__ xb, float* __restrict__ rstd, const float* __restrict__ x, int R, int H, float eps) {
+// Entry of a decoder run (and the pruned last layer): xb = act_t(x), rstd = 1/rms(x) for R fp32 rows.
+__global__ void rowprep_kernel(act_t* __restrict__ xb, float* __restrict__ rstd, const float* __restrict__ x, int R, int H, float eps) {
   const int r = blockIdx.x;
   if (r >= R) return;
   const float* src = x + static_cast<size_t>(r) * H;
@@ -110,10 +111,9 @@ __global__ void rowprep_kernel(__nv_bfloat16* __restrict__ xb, float* __restrict
   for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
     const float4 v = *reinterpret_cast<const float4*>(src + c);
     ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
     uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&a);
-    u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.x = Fmt16<act_t>::pack2(v.x, v.y);
+    u.y = Fmt16<act_t>::pack2(v.z, v.w);
     *reinterpret_cast<uint2*>(xb + static_cast<size_t>(r) * H + c) = u;
   }
   __shared__ float red[32];
@@ -126,11 +126,11 @@ __global__ void rowprep_kernel(__nv_bfloat16* __restrict__ xb, float* __restrict
     if (threadIdx.x == 0) rstd[r] = rsqrtf(v / static_cast<float>(H) + eps);
   }
 }
-// W[n, k] *= g[k] in place (bf16 weight, fp32 norm weight): folds an RMSNorm weight into the GEMM that consumes its output.
-__global__ void fold_norm_weight_kernel(__nv_bfloat16* __restrict__ w, const float* __restrict__ g, size_t rows, int cols) {
+// W[n, k] *= g[k] in place (operand-format weight, fp32 norm weight): folds an RMSNorm weight into the GEMM that consumes its output.
+__global__ void fold_norm_weight_kernel(act_t* __restrict__ w, const float* __restrict__ g, size_t rows, int cols) {
   const size_t n = rows * cols;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    w[i] = __float2bfloat16(__bfloat162float(w[i]) * g[i % cols]);
+    w[i] = Fmt16<act_t>::from_float(Fmt16<act_t>::to_float(w[i]) * g[i % cols]);
 }
 
 // copy selected fp32 rows: dst[r] = src[idx[r]]   (saves the last-prefix-token state of every prefix sequence)
@@ -142,46 +142,45 @@ __global__ void gather_rows_f32_kernel(float* __restrict__ dst, const float* __r
   for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) *reinterpret_cast<float4*>(d + c) = *reinterpret_cast<const float4*>(s + c);
 }
 
-// dst[r] = src[idx[r]] for bf16 rows of `w` elements (w % 8 == 0)
-__global__ void gather_rows_bf16_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ src, const int* __restrict__ idx,
-                                        int R, int w) {
+// dst[r] = src[idx[r]] for rows of `w` 16-bit elements of any format (w % 8 == 0)
+__global__ void gather_rows_16_kernel(void* __restrict__ dst, const void* __restrict__ src, const int* __restrict__ idx, int R, int w) {
   const int r = blockIdx.x;
   if (r >= R) return;
-  const __nv_bfloat16* s = src + static_cast<size_t>(idx[r]) * w;
-  __nv_bfloat16* d = dst + static_cast<size_t>(r) * w;
+  const uint16_t* s = reinterpret_cast<const uint16_t*>(src) + static_cast<size_t>(idx[r]) * w;
+  uint16_t* d = reinterpret_cast<uint16_t*>(dst) + static_cast<size_t>(r) * w;
   for (int c = threadIdx.x * 8; c < w; c += blockDim.x * 8) *reinterpret_cast<uint4*>(d + c) = *reinterpret_cast<const uint4*>(s + c);
 }
 
 // TVG visual rows: mean over the `group` tokens of a clip (reference: frame_feature.mean(1), modeling_videochat_flash.py:243),
-// fp32 accumulate, bf16 result.  in [R*group, H] -> out [R, H]
-__global__ void mean_rows_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ in, int R, int group, int H) {
+// fp32 accumulate, result in the activation format.  in [R*group, H] -> out [R, H]
+__global__ void mean_rows_kernel(act_t* __restrict__ out, const act_t* __restrict__ in, int R, int group, int H) {
   const int r = blockIdx.x;
   if (r >= R) return;
   for (int c = threadIdx.x * 2; c < H; c += blockDim.x * 2) {
     float a = 0.f, b = 0.f;
     for (int g = 0; g < group; ++g) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(in + (static_cast<size_t>(r) * group + g) * H + c));
+      const float2 f = Fmt16<act_t>::unpack2(*reinterpret_cast<const uint32_t*>(in + (static_cast<size_t>(r) * group + g) * H + c));
       a += f.x; b += f.y;
     }
-    *reinterpret_cast<__nv_bfloat162*>(out + static_cast<size_t>(r) * H + c) = __floats2bfloat162_rn(a / group, b / group);
+    *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(r) * H + c) = Fmt16<act_t>::pack2(a / group, b / group);
   }
 }
 
 // video_vocab built on the device from the stored features (reference: load_video_feature(vid).mean(1) per video,
 // dataloader/base_dataset.py:33-37): vocab[c][label[v]][:] = mean over the `group` tokens of clip c of video v.
-// grid = (n_videos * n_clips); feats [n_videos * n_clips * group, mm] bf16; vocab [n_clips][n_vocab][mm] bf16.
-__global__ void vocab_from_feats_kernel(__nv_bfloat16* __restrict__ vocab, const __nv_bfloat16* __restrict__ feats,
+// grid = (n_videos * n_clips); feats [n_videos * n_clips * group, mm]; vocab [n_clips][n_vocab][mm], both in the activation format.
+__global__ void vocab_from_feats_kernel(act_t* __restrict__ vocab, const act_t* __restrict__ feats,
                                         const int* __restrict__ labels, int n_clips, int group, int mm, int n_vocab) {
   const int v = blockIdx.x / n_clips, c = blockIdx.x % n_clips;
-  const __nv_bfloat16* src = feats + static_cast<size_t>(blockIdx.x) * group * mm;
-  __nv_bfloat16* dst = vocab + (static_cast<size_t>(c) * n_vocab + labels[v]) * mm;
+  const act_t* src = feats + static_cast<size_t>(blockIdx.x) * group * mm;
+  act_t* dst = vocab + (static_cast<size_t>(c) * n_vocab + labels[v]) * mm;
   for (int d = threadIdx.x * 2; d < mm; d += blockDim.x * 2) {
     float a = 0.f, b = 0.f;
     for (int g = 0; g < group; ++g) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + static_cast<size_t>(g) * mm + d));
+      const float2 f = Fmt16<act_t>::unpack2(*reinterpret_cast<const uint32_t*>(src + static_cast<size_t>(g) * mm + d));
       a += f.x; b += f.y;
     }
-    *reinterpret_cast<__nv_bfloat162*>(dst + d) = __floats2bfloat162_rn(a / group, b / group);
+    *reinterpret_cast<uint32_t*>(dst + d) = Fmt16<act_t>::pack2(a / group, b / group);
   }
 }
 
@@ -256,13 +255,14 @@ __device__ __forceinline__ float load_as_f32(const void* src, int dtype, size_t 
   if (dtype == 1) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
   return __half2float(reinterpret_cast<const __half*>(src)[i]);
 }
-__global__ void repack_rows_bf16_kernel(__nv_bfloat16* __restrict__ dst, const void* __restrict__ src, int dtype, int rows, int cols,
-                                        int dst_row0, int interleave, int half) {
+template <typename T>   // T = act_t (GEMM operands: weights, features) or __nv_bfloat16 (embedding table, the extractor)
+__global__ void repack_rows_16_kernel(T* __restrict__ dst, const void* __restrict__ src, int dtype, int rows, int cols,
+                                      int dst_row0, int interleave, int half) {
   const size_t n = static_cast<size_t>(rows) * cols;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
     const int dr = interleave > 0 ? (r / interleave) * 2 * interleave + half * interleave + r % interleave : dst_row0 + r;
-    dst[static_cast<size_t>(dr) * cols + c] = __float2bfloat16(load_as_f32(src, dtype, i));
+    dst[static_cast<size_t>(dr) * cols + c] = Fmt16<T>::from_float(load_as_f32(src, dtype, i));
   }
 }
 // fp32 destination.  round_bf16 != 0 rounds through bf16 first (parameters that live in the model dtype in the reference).
@@ -273,14 +273,14 @@ __global__ void repack_f32_kernel(float* __restrict__ dst, const void* __restric
     dst[i] = v;
   }
 }
-// video_vocab [N_v, n_clips, MM] -> [n_clips, N_v, MM] bf16 (one K-major B operand per clip)
-__global__ void repack_vocab_kernel(__nv_bfloat16* __restrict__ dst, const void* __restrict__ src, int dtype, int n_v, int n_clips, int mm) {
+// video_vocab [N_v, n_clips, MM] -> [n_clips, N_v, MM] in the activation format (one K-major B operand per clip)
+__global__ void repack_vocab_kernel(act_t* __restrict__ dst, const void* __restrict__ src, int dtype, int n_v, int n_clips, int mm) {
   const size_t n = static_cast<size_t>(n_v) * n_clips * mm;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int d = static_cast<int>(i % mm);
     const int c = static_cast<int>((i / mm) % n_clips);
     const int u = static_cast<int>(i / (static_cast<size_t>(mm) * n_clips));
-    dst[(static_cast<size_t>(c) * n_v + u) * mm + d] = __float2bfloat16(load_as_f32(src, dtype, i));
+    dst[(static_cast<size_t>(c) * n_v + u) * mm + d] = Fmt16<act_t>::from_float(load_as_f32(src, dtype, i));
   }
 }
 
@@ -306,11 +306,11 @@ __global__ void scatter_scores_kernel(float* __restrict__ dense, int n_cols, con
 // Replicate the K/V rows [0, n_rows) of every layer of the prefix cache to rows [dst[u], dst[u] + n_rows) for every unit u:
 // the shared "root" of the prefixes (chat-template header) is prefilled once and copied in front of each unit's own rows.
 // grid = (n_units, n_layers, 2 [K, V]); w = row width in elements (w % 8 == 0).
-__global__ void replicate_root_rows_kernel(__nv_bfloat16* __restrict__ kp, __nv_bfloat16* __restrict__ vp, const int* __restrict__ dst,
+__global__ void replicate_root_rows_kernel(act_t* __restrict__ kp, act_t* __restrict__ vp, const int* __restrict__ dst,
                                            int n_rows, int w, size_t layer_stride) {
-  __nv_bfloat16* base = (blockIdx.z == 0 ? kp : vp) + static_cast<size_t>(blockIdx.y) * layer_stride;
-  const __nv_bfloat16* src = base;
-  __nv_bfloat16* out = base + static_cast<size_t>(dst[blockIdx.x]) * w;
+  act_t* base = (blockIdx.z == 0 ? kp : vp) + static_cast<size_t>(blockIdx.y) * layer_stride;
+  const act_t* src = base;
+  act_t* out = base + static_cast<size_t>(dst[blockIdx.x]) * w;
   const int n = n_rows * (w / 8);
   for (int i = threadIdx.x; i < n; i += blockDim.x) reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(src)[i];
 }

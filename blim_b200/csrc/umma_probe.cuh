@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "act_type.cuh"
 #include "ptx_sm100.cuh"
 
 namespace blim {
@@ -30,16 +31,11 @@ __host__ __device__ inline uint64_t make_smem_desc_raw(uint32_t smem_addr, uint3
   return d;
 }
 
-// idesc with runtime N and B major-ness (bit 16: 0 = K-major, 1 = MN-major)
-__host__ __device__ inline uint32_t make_idesc_bf16_ex(int m, int n, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
-}
 
 // A: [128][K] bf16 row-major (K = 64 or 128).  B: b_mn_major ? [K][N] : [N][K] row-major, N = 64 or 128.  C: [128][N] fp32.
 __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
                                                            float* __restrict__ C, int K, int N, int b_mn_major, uint32_t lbo, uint32_t sbo,
-                                                           uint32_t kstep_bytes) {
+                                                           uint32_t kstep_bytes, int a_fmt, int b_fmt) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* s_a = smem;                 // K/64 sub-tiles of [128 x 64]
@@ -78,7 +74,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __nv_bfloat16*
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   if (tid == 0) {
-    const uint32_t idesc = make_idesc_bf16_ex(128, N, b_mn_major);
+    const uint32_t idesc = make_idesc_f16kind(128, N, a_fmt, b_fmt, b_mn_major);
     for (int k = 0; k < K / 16; ++k) {
       const uint64_t da = make_smem_desc_sw128(smem_u32(s_a) + (k >> 2) * 16384 + (k & 3) * 32);
       uint64_t db;
@@ -102,18 +98,18 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __nv_bfloat16*
   if (warp == 0) tmem_dealloc<1>(tmem, 128);
 }
 
+// b_mn_major: bit 0 = B is MN-major; bit 1 = A holds fp16 (else bf16); bit 2 = B holds fp16 -- the two operand formats of
+// kind::f16 are independent, which the scoring path relies on (fp16 activations x bf16 weights).
 inline cudaError_t launch_umma_probe(const void* A, const void* B, float* C, int K, int N, int b_mn_major, uint32_t lbo, uint32_t sbo,
                                      uint32_t kstep_bytes, cudaStream_t st) {
+  const int a_fmt = (b_mn_major & 2) ? kFmtF16 : kFmtBF16, b_fmt = (b_mn_major & 4) ? kFmtF16 : kFmtBF16;
+  b_mn_major &= 1;
   if ((K != 64 && K != 128) || (N != 64 && N != 128)) return cudaErrorInvalidValue;
   const int smem = 1024 + 4 * 16384;
-  static bool set = false;
-  if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    set = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
   umma_probe_kernel<<<1, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(A), reinterpret_cast<const __nv_bfloat16*>(B), C, K, N,
-                                          b_mn_major, lbo, sbo, kstep_bytes);
+                                          b_mn_major, lbo, sbo, kstep_bytes, a_fmt, b_fmt);
   return cudaGetLastError();
 }
 

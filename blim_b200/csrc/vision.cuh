@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(256) layernorm_warp_kernel(OutT* __restrict__ 
     const float y0 = v[i].x * rstd * g.x + h.x, y1 = v[i].y * rstd * g.y + h.y, y2 = v[i].z * rstd * g.z + h.z, y3 = v[i].w * rstd * g.w + h.w;
     if constexpr (sizeof(OutT) == 2) {
       uint2 u;
-      u.x = pack_bf16x2(y0, y1);
-      u.y = pack_bf16x2(y2, y3);
+      u.x = Fmt16<__nv_bfloat16>::pack2(y0, y1);
+      u.y = Fmt16<__nv_bfloat16>::pack2(y2, y3);
       reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * C)[lane + 32 * i] = u;
     } else {
       reinterpret_cast<float4*>(out + static_cast<size_t>(row) * C)[lane + 32 * i] = make_float4(y0, y1, y2, y3);
@@ -454,8 +454,8 @@ extern "C" int blim_vision_create(const blim_vision_cfg* cfg, int device, blim_v
   v->gemm.num_sms = prop.multiProcessorCount;
   v->gemm.device = device;
   v->gemm.cta_group = 2;
-  v->attn_version = dh == 64 ? 4 : 2;   // v4 (issue warp, two P tiles) wins at head_dim 64; at 128 its 96-register budget spills
-  if (const char* a = getenv("BLIM_VIS_ATTN")) v->attn_version = (atoi(a) >= 2 && atoi(a) <= 4) ? atoi(a) : v->attn_version;
+  v->attn_version = dh == 64 ? kAttnIssueWarp : kAttnPerItem;   // v4 (issue warp, two P tiles) wins at head_dim 64; at 128 its 96-register budget spills
+  if (const char* a = getenv("BLIM_VIS_ATTN")) v->attn_version = atoi(a) == 4 ? kAttnIssueWarp : atoi(a) == 2 ? kAttnPerItem : v->attn_version;
   v->blocks.resize(v->NL);
   const size_t M = static_cast<size_t>(v->max_clips) * v->TL;
   const size_t na = (v->TL + 1) / 2;
@@ -480,7 +480,7 @@ extern "C" int blim_vision_create(const blim_vision_cfg* cfg, int device, blim_v
 // ------------------------------------------------------------------------------------------------ weights
 static int vis_copy_bf16(blim_vision* v, DevBuf& dst, const void* src, int dtype, size_t rows, size_t cols, cudaStream_t st) {
   VCK(dst.reserve(rows * cols * 2));
-  repack_rows_bf16_kernel<<<1024, 256, 0, st>>>(dst.as<bf16>(), src, dtype, static_cast<int>(rows), static_cast<int>(cols), 0, 0, 0);
+  repack_rows_16_kernel<bf16><<<1024, 256, 0, st>>>(dst.as<bf16>(), src, dtype, static_cast<int>(rows), static_cast<int>(cols), 0, 0, 0);
   VCL();
   return 0;
 }
@@ -648,7 +648,7 @@ static int vis_encode(blim_vision* v, const void* frames, int dtype, int n_frame
       if (vis_gemm<EpiStore<bf16, true, false>>(v, xn, C, w.w_qkv.as<bf16>(), C, M, 3 * C, C, p, st)) return 1;
     }
     v->tic(1, st);
-    cudaError_t r = launch_attention_tc(maps, ap, v->n_works, v->NH, v->DH, st, v->attn_version);
+    cudaError_t r = launch_attention_tc<bf16>(maps, ap, v->n_works, v->NH, v->DH, st, v->attn_version);
     v->toc(st);
     if (r != cudaSuccess) return v->fail_cuda("attention launch", r);
     v->launches++;

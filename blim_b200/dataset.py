@@ -219,7 +219,7 @@ class StagedCorpus:
 
 def stage_corpus(model, dataset, pin=True):
     """Device-side input pipeline: every item's feature file is read ONCE into one pinned host tensor `[N, n_clips, 64, MM]`
-    (bf16), uploaded with a single asynchronous copy, the video vocabulary `feature.mean(1)` of the sorted video ids is
+    (in the files' own 16-bit dtype -- fp16 in the reference, extract.py:107-110 -- so nothing is re-rounded), uploaded with a single asynchronous copy, the video vocabulary `feature.mean(1)` of the sorted video ids is
     reduced on the device (blim_build_video_vocab), and both token tables go to the engine as flat ragged arrays.  After
     this call score_pairs / evaluation need no per-row host work (reference: per-row list comprehension + H2D copies,
     retrieval_utils.py:55-60, and one torch.load per __getitem__ plus one per vocabulary entry, base_dataset.py:26-37)."""
@@ -228,7 +228,7 @@ def stage_corpus(model, dataset, pin=True):
     n = len(dataset)
     first = dataset.load_video_feature(dataset.data[0]["vid"])
     n_clips = first.shape[0]
-    host = torch.empty((n,) + tuple(first.shape), dtype=torch.bfloat16)
+    host = torch.empty((n,) + tuple(first.shape), dtype=first.dtype if first.dtype in (torch.float16, torch.bfloat16) else torch.float16)
     if pin and torch.cuda.is_available():
         host = host.pin_memory()
     vtg, tvg, labels = [], [], []

@@ -80,6 +80,8 @@ class Engine:
         self.h = h
         self._keep = {}
         self.n_clips = 0
+        # 16-bit format of the engine's tensor-core operands (fp16 by default, csrc/act_type.cuh)
+        self.act_dtype = {1: torch.bfloat16, 2: torch.float16}[int(self.lib.blim_act_dtype())]
 
     # ---------------------------------------------------------------- helpers
     def _check(self, rc):
@@ -337,30 +339,35 @@ class Engine:
         return {k: dict(ms=ms[i], flops=fl[i], launches=ln[i]) for i, k in enumerate(self.PROFILE_KINDS)}
 
     def debug_umma(self, A, B, b_mn_major, lbo=0, sbo=0, kstep=0):
-        """Single-CTA tcgen05 probe (see blim_debug_umma): A [128, K] bf16, B [N, K] or (b_mn_major) [K, N] bf16 -> fp32 [128, N]."""
+        """Single-CTA tcgen05 probe (see blim_debug_umma): A [128, K], B [N, K] or (b_mn_major) [K, N] -> fp32 [128, N].
+        Each operand is passed in its own 16-bit format (torch.float16 stays fp16, anything else becomes bf16)."""
         with torch.cuda.device(self.device):
-            A, B = self._dev(A, torch.bfloat16), self._dev(B, torch.bfloat16)
+            fa = torch.float16 if A.dtype == torch.float16 else torch.bfloat16
+            fb = torch.float16 if B.dtype == torch.float16 else torch.bfloat16
+            A, B = self._dev(A, fa), self._dev(B, fb)
             K = A.shape[1]
             N = B.shape[1] if b_mn_major else B.shape[0]
             C = torch.zeros(128, N, dtype=torch.float32, device=self.device)
+            flags = int(bool(b_mn_major)) | (2 if fa == torch.float16 else 0) | (4 if fb == torch.float16 else 0)
             self._check(self.lib.blim_debug_umma(self.h, ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()),
-                                                 ctypes.c_void_p(C.data_ptr()), K, N, int(b_mn_major), lbo, sbo, kstep, self._stream()))
+                                                 ctypes.c_void_p(C.data_ptr()), K, N, flags, lbo, sbo, kstep, self._stream()))
         return C
 
     def debug_gemm(self, epilogue, A, W, bias=None, target=None, scale=1.0, cta_group=0, C=None):
-        """Unit-test entry for the tcgen05 GEMM core (see blim_debug_gemm)."""
+        """Unit-test entry for the tcgen05 GEMM core (see blim_debug_gemm): A and W are converted to the engine's operand
+        format; 16-bit results come back in that format."""
         with torch.cuda.device(self.device):
-            A = self._dev(A, torch.bfloat16)
-            W = self._dev(W, torch.bfloat16)
+            A = self._dev(A, self.act_dtype)
+            W = self._dev(W, self.act_dtype)
             M, K = A.shape
             N = W.shape[0]
             if C is None:
                 if epilogue in (0, 1, 2):
-                    C = torch.empty(M, N, dtype=torch.bfloat16, device=self.device)
+                    C = torch.empty(M, N, dtype=self.act_dtype, device=self.device)
                 elif epilogue == 3:
                     C = torch.empty(M, N, dtype=torch.float32, device=self.device)
                 elif epilogue == 5:
-                    C = torch.empty(M, N // 2, dtype=torch.bfloat16, device=self.device)
+                    C = torch.empty(M, N // 2, dtype=self.act_dtype, device=self.device)
                 elif epilogue == 6:
                     C = torch.empty(M, dtype=torch.float32, device=self.device)
                 else:

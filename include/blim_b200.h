@@ -146,16 +146,24 @@ int blim_profile_read(blim_engine* e, double* gemm_ms, double* attn_ms, int64_t*
  * of the GEMM launches (0 for attention / RMSNorm). */
 int blim_profile_read_detail(blim_engine* e, int n, double* ms, double* flops, int64_t* launches);
 
-/* Debug / unit-test entry: C = epilogue(A[M,K] · W[N,K]^T) with the engine's tcgen05 GEMM.
- * epilogue: 0 = bf16 store, 1 = bf16 store + bias, 2 = bf16 store + bias + GELU, 3 = fp32 store,
- *           4 = fp32 residual add (C += A·W^T), 5 = SwiGLU (W = 128-row interleaved gate|up, C bf16 [M, N/2]),
+/* 16-bit format of the engine's tensor-core operands (weights as stored after blim_load_weight, activations), in
+ * blim_load_weight's dtype codes: 2 = fp16 (default build), 1 = bf16 (-DBLIM_ACT_BF16); see csrc/act_type.cuh.  Only the
+ * debug entries below expose operand-format buffers; every other entry point speaks the dtypes documented with it. */
+int blim_act_dtype(void);
+
+/* Debug / unit-test entry: C = epilogue(A[M,K] · W[N,K]^T) with the engine's tcgen05 GEMM.  A and W are in the operand
+ * format (blim_act_dtype); "act" outputs are in that format too.
+ * epilogue: 0 = act store, 1 = act store + bias, 2 = act store + bias + GELU, 3 = fp32 store,
+ *           4 = fp32 residual add (C += A·W^T), 5 = SwiGLU (W = 128-row interleaved gate|up, C act [M, N/2]),
  *           6 = log-sum-exp (C fp32 [M]: logp of target[M] at `scale`). */
 int blim_debug_gemm(blim_engine* e, int epilogue, const void* A, const void* W, void* C, int M, int N, int K, const float* bias,
                     const int32_t* target, float scale, int cta_group, void* stream);
 
 /* Debug / unit-test entry: single-CTA tcgen05 probe C[128,N] = A[128,K] · B with thread-staged (manually swizzled)
- * operands; B is [N][K] (K-major) or, with b_mn_major, [K][N] with explicit descriptor byte offsets.  Pins the
- * shared-memory descriptor semantics the attention kernel relies on (tests/test_umma_probe_gpu.py). */
+ * operands; B is [N][K] (K-major) or, with bit 0 of b_mn_major, [K][N] with explicit descriptor byte offsets.  Bit 1 of
+ * b_mn_major: A holds fp16 instead of bf16; bit 2: B holds fp16.  Pins the shared-memory descriptor semantics the
+ * attention kernel relies on, and that both operands of an MMA must share one format
+ * (tests/test_umma_probe_gpu.py). */
 int blim_debug_umma(blim_engine* e, const void* A, const void* B, float* C, int K, int N, int b_mn_major, uint32_t lbo, uint32_t sbo,
                     uint32_t kstep_bytes, void* stream);
 

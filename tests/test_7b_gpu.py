@@ -1,7 +1,7 @@
-"""Full-size (VideoChat-Flash-Qwen2-7B architecture, random init) parity and property tests.  GPU only, ~2 minutes.
+"""Full-size (VideoChat-Flash-Qwen2-7B architecture, random init) parity and property tests.  GPU only, ~3 minutes.
 
- * engine vs the oracle (reference algorithm restated in plain PyTorch, fp32, run on the GPU for speed) on a handful of
-   pairs of every score kind: |d log-likelihood| <= 1e-2 (BASELINE.json north_star tolerance for the bf16 pipeline);
+ * engine vs the unmodified reference run on the GPU in fp32 and in bf16, 256 pairs of every score matrix:
+   |d log-likelihood| <= 1e-2 against the fp32 run (BASELINE.json north_star tolerance), fixed bounds against the bf16 run;
  * size-independent properties on MSRVTT-shaped data: re-batching invariance (a pair's score does not depend on
    which other pairs share its decoder run) and direction symmetry of the deduplicated pair set."""
 import numpy as np
@@ -43,37 +43,69 @@ def _set_corpus(model, corpus):
     model.set_tvg_prefix_length(corpus.tvg_prefix_length)
 
 
-def test_7b_scores_match_oracle(seven_b):
+def test_7b_scores_match_reference(seven_b):
+    """256 pairs of every one of the six score matrices (16 rows x top-16 of an MSRVTT-1k-shaped corpus) against the
+    UNMODIFIED reference run on this GPU (oracle/ref_gpu.py; sources shipped in baseline/_ref by build()):
+
+      * engine vs the reference in fp32 (the exact value): |d log-likelihood| <= 1e-2 for every pair -- the north-star
+        tolerance, asserted as a fixed bound;
+      * engine vs the reference in bf16 (autocast, sdpa, batch 16 -- the reference's own reduced-precision path): that
+        run itself sits up to 5e-2 from the reference's fp32 run (profiles/r02_parity_7b_*.json), so the bound here is
+        what two correct 16-bit pipelines can differ by: 8e-2 (VTG kinds) / 2.5e-2 (TVG kinds);
+      * the engine is closer to the exact value than the reference's bf16 run is, per kind, in the mean;
+      * reranked candidate order of the fused BLiM scores vs the fp32 reference: only candidates whose exact fused scores
+        are closer than 2e-2 may swap, ground-truth ranks / top-1 agree wherever the exact top-1 margin exceeds 2e-2."""
+    from oracle import ref_gpu, ref_harness
     cfg, model, weights = seven_b
-    corpus = synth.make_corpus(cfg, "msrvtt", n=6, seed=5)
+    rows, topk = 16, 16
+    corpus = synth.make_corpus(cfg, "msrvtt", n=1000, seed=5)
     _set_corpus(model, corpus)
-    p = {k: v.float() for k, v in weights.items()}   # fp32 copy of the same bf16 values (~30 GB)
-    worst, worst_bf16 = {}, {}
-    try:
-        for direction in ("v2t", "t2v"):
-            for ft, cpn in (("vtg", False), ("vtg", True), ("tvg", False), ("tvg", True)):
-                with torch.no_grad():
-                    ref = O.compute_scores_x(p, cfg, corpus, direction, ft, cpn, topk=3, batch_size=3, rows=[0, 2, 4], device="cuda").numpy()
-                    # the same algorithm with bf16 weights/activations through PyTorch (cuBLAS, SDPA-equivalent eager maths):
-                    # how far a bf16 run of the reference itself sits from its fp32 run on these pairs
-                    ref16 = O.compute_scores_x(weights, cfg, corpus, direction, ft, cpn, topk=3, batch_size=3, rows=[0, 2, 4], device="cuda").numpy()
-                rows, cols = np.nonzero(ref != -100.0)
-                pv, pt = (rows, cols) if direction == "v2t" else (cols, rows)
-                got = model.engine.score_pairs(KIND[(ft, cpn)], pv, pt).cpu().numpy()
-                err = float(np.abs(got - ref[rows, cols]).max())
-                err16 = float(np.abs(ref16[rows, cols] - ref[rows, cols]).max())
-                worst[(direction, ft, cpn)] = round(err, 5)
-                worst_bf16[(direction, ft, cpn)] = round(err16, 5)
-                assert np.isfinite(got).all()
-    finally:
+    m_eng = ref_gpu.engine_matrices(model.engine, corpus, 0, rows, topk)
+    if ref_harness.reference_available():
+        rr = ref_gpu.ReferenceRunner(cfg, weights, corpus, "cuda:0", dtype=torch.bfloat16)
+        m_b16, secs, pairs = rr.all_matrices(0, rows, topk)
+        rr.close()
+        del rr
+        rr = ref_gpu.ReferenceRunner(cfg, weights, corpus, "cuda:0", dtype=torch.float32)
+        m_f32, _, _ = rr.all_matrices(0, rows, topk)
+        rr.close()
+        del rr
+        print(f"reference (bf16, sdpa, batch 16) on this GPU: {pairs / secs:.1f} pairs/s")
+    else:   # no shipped reference: the oracle restatement (pinned to the reference by tests/golden) is the fp32 comparator
+        m_b16 = None
+        p = {k: v.float() for k, v in weights.items()}
+        m_f32 = {}
+        for name, (direction, ft, cpn) in ref_gpu.MATRICES.items():
+            with torch.no_grad():
+                dense = O.compute_scores_x(p, cfg, corpus, direction, ft, cpn, topk=topk, batch_size=16, rows=range(rows), device="cuda").numpy()
+            idx = m_eng[name][0]
+            m_f32[name] = (idx, np.take_along_axis(dense[:rows], idx, 1))
         del p
-        torch.cuda.empty_cache()
-    print("7B engine   max |d| vs fp32 oracle per kind:", worst)
-    print("7B bf16-ref max |d| vs fp32 oracle per kind:", worst_bf16)
-    for k, err in worst.items():
-        # tolerance: 1e-2 absolute (BASELINE.json north_star); where a bf16 run of the reference algorithm itself deviates
-        # more than that from fp32 on the same pairs, the engine must at least be as close as that bf16 run
-        assert err <= max(1e-2, worst_bf16[k]), f"{k}: engine |d|={err}, bf16 reference |d|={worst_bf16[k]}"
+    torch.cuda.empty_cache()
+    worst = {}
+    for name in ref_gpu.MATRICES:
+        e, f = m_eng[name][1], m_f32[name][1]
+        assert np.isfinite(e).all()
+        row = {"engine_vs_fp32": float(np.abs(e - f).max()), "engine_vs_fp32_mean": float(np.abs(e - f).mean())}
+        if m_b16 is not None:
+            b = m_b16[name][1]
+            row.update(engine_vs_bf16=float(np.abs(e - b).max()), bf16_vs_fp32=float(np.abs(b - f).max()), bf16_vs_fp32_mean=float(np.abs(b - f).mean()))
+        worst[name] = {k: round(v, 5) for k, v in row.items()}
+    for name, row in worst.items():
+        print("7B", name, row)
+    for name, row in worst.items():
+        tvg = ref_gpu.MATRICES[name][1] == "tvg"
+        assert row["engine_vs_fp32"] <= 1e-2, f"{name}: engine is {row['engine_vs_fp32']} from the fp32 reference"
+        if m_b16 is not None:
+            assert row["engine_vs_bf16"] <= (2.5e-2 if tvg else 8e-2), f"{name}: engine is {row['engine_vs_bf16']} from the bf16 reference"
+            assert row["engine_vs_fp32_mean"] <= row["bf16_vs_fp32_mean"], f"{name}: the reference's bf16 run is closer to fp32 than the engine"
+    alpha, c = (0.0, 0.8), (1.0, 0.6, 0.8, 0.4)
+    rp = ref_gpu.rank_parity(ref_gpu.fused_rows(m_f32, corpus, 0, rows, alpha, c), ref_gpu.fused_rows(m_eng, corpus, 0, rows, alpha, c))
+    print("7B rank parity vs the fp32 reference:", rp)
+    for d, r in rp.items():
+        assert r["max_gap_of_swapped_pairs_a"] <= 2e-2, (d, r)
+        if r["min_top1_margin_a"] > 2e-2:
+            assert r["rows_same_top1"] == r["rows"] and r["recall_equal"], (d, r)
 
 
 def test_7b_rebatching_invariance_and_symmetry(seven_b):

@@ -249,12 +249,14 @@ def test_topk_rows_matches_torch():
 
 
 def test_device_built_video_vocab_matches_uploaded(golden_case):
-    """blim_build_video_vocab (mean over the 64 tokens on the device) gives the same TVG scores as the uploaded vocab."""
+    """blim_build_video_vocab (mean over the 64 tokens on the device) gives the same TVG scores as the uploaded vocab, up to
+    the rounding of the vocabulary itself: the uploaded one was rounded to bf16 on the host (synth.make_corpus), the
+    device-built one goes straight to the engine's operand format."""
     name, spec, cfg, weights, corpus, eng, gold = golden_case
     ref = gold["t2v_tvg_lik"]
     rows, cols = np.nonzero(ref != -100.0)
     a = eng.score_pairs(TVG, cols, rows).cpu().numpy()
     eng.build_video_vocab(corpus.tvg_video_labels.numpy())
     b = eng.score_pairs(TVG, cols, rows).cpu().numpy()
-    assert np.array_equal(a, b)
+    assert np.abs(a - b).max() <= 1e-3, np.abs(a - b).max()
     eng.set_video_vocab(corpus.video_vocab, corpus.tvg_video_labels.numpy())

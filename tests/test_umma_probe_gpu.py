@@ -46,3 +46,16 @@ def test_mn_major_b_descriptor(eng, K, N):
         report[name] = (got - ref).abs().max().item()
     print(f"K={K} N={N}:", {k: round(v, 4) for k, v in report.items()})
     assert report["lbo=tile,sbo=1024,k=2048"] < 1e-3 * max(1.0, ref.abs().max().item()), report
+
+
+def test_fp16_operands(eng):
+    """kind::f16 with both operands in fp16 (the scoring path's operand format): values use the full 11-bit significand,
+    so reading the fp16 bits as bf16 cannot pass.  (Mixed fp16 x bf16 operands are NOT supported by the hardware: the
+    MMA raises an illegal-instruction error, measured on B200 -- which is why weights are converted to fp16 at load.)"""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = (torch.randn(128, 128, generator=g, device="cuda") * 0.5).half()
+    B = (torch.randn(64, 128, generator=g, device="cuda") * 0.5).half()
+    ref = A.float() @ B.float().t()
+    got = eng.debug_umma(A, B, b_mn_major=False)
+    torch.cuda.synchronize()
+    assert (got - ref).abs().max() < 1e-4 * max(1.0, ref.abs().max().item()), (got - ref).abs().max().item()
