@@ -82,6 +82,10 @@ SIGNATURES = {
     "blim_rank_dense": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "blim_topk_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "blim_scatter_scores": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_f32, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "blim_comm_unique_id": (c_int, [c_void_p]),
+    "blim_comm_init": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "blim_comm_destroy": (c_int, [c_void_p]),
+    "blim_allgather_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "blim_act_dtype": (c_int, []),
     "blim_kernel_launches": (c_i64, [c_void_p]),
     "blim_gemm_flops": (c_f64, [c_void_p]),

@@ -40,10 +40,12 @@ def seed_tvg_mlp(state_dict):
     return state_dict
 
 
-def merge_lora(base_state_dict, trainable_state_dict, lora_r, lora_alpha, dtype=torch.bfloat16, tvg_from_mlp=True):
+def merge_lora(base_state_dict, trainable_state_dict, lora_r, lora_alpha, dtype=torch.float16, tvg_from_mlp=True):
     """Returns a new state dict: base weights with every LoRA pair merged (W + alpha/r * B @ A) and every other tensor of
     the checkpoint (visual_head.weight, ...) overriding the base tensor of the same plain name.  `tvg_from_mlp`: the
-    tvg_mlp adapters sit on a copy of the base mlp (see seed_tvg_mlp), not on whatever tvg_mlp the base dict carries."""
+    tvg_mlp adapters sit on a copy of the base mlp (see seed_tvg_mlp), not on whatever tvg_mlp the base dict carries.
+    `dtype` of the merged tensors: fp16 by default -- the engine's operand format (csrc/act_type.cuh) and the precision the
+    reference itself runs the adapters in (main.py:97); bf16 would round away adapter deltas below 2^-8 of the weight."""
     scale = float(lora_alpha) / float(lora_r)
     out = {_plain_name(k): v for k, v in base_state_dict.items()}
     if tvg_from_mlp:

@@ -26,6 +26,7 @@
 #include "../../include/blim_b200.h"
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "comm.cuh"
 #include "gemm_sm100.cuh"
 #include "kernels_misc.cuh"
 #include "umma_probe.cuh"
@@ -163,6 +164,8 @@ struct blim_engine {
   size_t arena_cap = 0, arena_off = 0;
   bool arena_disabled = false;
   bool root_share = true;   // shared prompt-header root for the prefixes (BLIM_ROOT=0 disables)
+  NcclComm comm = nullptr;   // blim_comm_init: this engine's NCCL communicator (one rank per engine / process / GPU)
+  int comm_rank = 0, comm_world = 1;
   bool attr_fuse = false, attr_topk = false;   // cudaFuncSetAttribute done on this engine's device
   bool fuse_norm = false;  // BLIM_FUSE_NORM=1: RMSNorm fused into the GEMMs around it (measured slower than the standalone kernel)
   DevBuf ssq, rstd;
@@ -268,6 +271,7 @@ extern "C" void blim_destroy(blim_engine* e) {
     l.w_qkv.release(); l.w_o.release(); l.w_gu.release(); l.w_down.release(); l.b_qkv.release(); l.ln1.release(); l.ln2.release();
   }
   for (ProjW& p : e->proj) { p.w0.release(); p.b0.release(); p.w2.release(); p.b2.release(); }
+  if (e->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(e->comm);
   if (e->arena) cudaFreeHost(e->arena);
   for (auto& t : e->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
@@ -1541,6 +1545,63 @@ extern "C" int blim_profile_read_detail(blim_engine* e, int n, double* ms, doubl
 extern "C" int blim_act_dtype(void) { return kActFmt == kFmtF16 ? 2 : 1; }
 extern "C" int64_t blim_kernel_launches(const blim_engine* e) { return e ? e->launches + e->gemm.launches : 0; }
 extern "C" double blim_gemm_flops(const blim_engine* e) { return e ? e->flops : 0.0; }
+
+// ------------------------------------------------------------------------------------------------ multi-GPU exchange
+extern "C" int blim_comm_unique_id(void* id_out128) {
+  if (!id_out128) { g_create_error = "null argument"; return 1; }
+  NcclApi& api = nccl_api();
+  if (!api.load()) { g_create_error = api.error; return 1; }
+  NcclUniqueId id;
+  const int rc = api.GetUniqueId(&id);
+  if (rc != kNcclSuccess) { g_create_error = "ncclGetUniqueId: " + api.describe(rc); return 1; }
+  memcpy(id_out128, id.internal, sizeof(id.internal));
+  return 0;
+}
+
+extern "C" int blim_comm_init(blim_engine* e, const void* id128, int rank, int world) {
+  if (!e) return 1;
+  if (!id128 || world <= 0 || rank < 0 || rank >= world) return e->fail("bad communicator arguments");
+  if (e->comm) return e->fail("communicator already initialised");
+  NcclApi& api = nccl_api();
+  if (!api.load()) return e->fail(api.error);
+  CKE(cudaSetDevice(e->device));
+  NcclUniqueId id;
+  memcpy(id.internal, id128, sizeof(id.internal));
+  const int rc = api.CommInitRank(&e->comm, world, id, rank);
+  if (rc != kNcclSuccess) { e->comm = nullptr; return e->fail("ncclCommInitRank: " + api.describe(rc)); }
+  e->comm_rank = rank;
+  e->comm_world = world;
+  return 0;
+}
+
+extern "C" int blim_comm_destroy(blim_engine* e) {
+  if (!e) return 1;
+  if (e->comm) {
+    CKE(cudaSetDevice(e->device));
+    nccl_api().CommDestroy(e->comm);
+    e->comm = nullptr;
+    e->comm_world = 1;
+    e->comm_rank = 0;
+  }
+  return 0;
+}
+
+// recv[r * count .. (r + 1) * count) = rank r's send[0 .. count) for every rank r, fp32, enqueued on `stream` behind the
+// scoring kernels that produce `send` (no host synchronisation).  nccl_comm: an ncclComm_t owned by the caller, or
+// nullptr for the engine's own communicator (blim_comm_init).
+extern "C" int blim_allgather_scores(blim_engine* e, void* nccl_comm, const float* send_dev, float* recv_dev, int64_t count_per_rank, void* stream) {
+  if (!e) return 1;
+  if (!send_dev || !recv_dev || count_per_rank < 0) return e->fail("bad all-gather arguments");
+  if (count_per_rank == 0) return 0;
+  NcclApi& api = nccl_api();
+  if (!api.load()) return e->fail(api.error);
+  NcclComm comm = nccl_comm ? reinterpret_cast<NcclComm>(nccl_comm) : e->comm;
+  if (!comm) return e->fail("no communicator: call blim_comm_init or pass an ncclComm_t");
+  CKE(cudaSetDevice(e->device));
+  const int rc = api.AllGather(send_dev, recv_dev, static_cast<size_t>(count_per_rank), kNcclFloat32, comm, S(stream));
+  if (rc != kNcclSuccess) return e->fail("ncclAllGather: " + api.describe(rc));
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------ debug GEMM entry
 extern "C" int blim_debug_gemm(blim_engine* e, int epilogue, const void* A, const void* W, void* C, int M, int N, int K, const float* bias,

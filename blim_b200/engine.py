@@ -257,6 +257,37 @@ class Engine:
                                                    self._stream()))
         return out.reshape(*ids.shape, self.cfg.hidden_size)
 
+    # ---------------------------------------------------------------- multi-GPU exchange
+    comm_world = 1
+
+    def comm_init(self, group=None):
+        """Join this engine's NCCL communicator (one engine per rank): rank 0 creates the unique id, torch.distributed only
+        carries its 128 bytes to the other ranks; the all-gather itself runs in the engine on the compute stream."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if self.comm_world == world and world > 1:
+            return
+        box = [None]
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            if self.lib.blim_comm_unique_id(buf) != 0:
+                raise EngineError(self.lib.blim_last_error(None).decode())
+            box[0] = bytes(buf.raw)
+        dist.broadcast_object_list(box, src=0, group=group)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.blim_comm_init(self.h, ctypes.c_char_p(box[0]), rank, world))
+        self.comm_world = world
+
+    def allgather_scores(self, send, recv=None):
+        """recv[r * n : (r + 1) * n] = rank r's send (fp32 device tensors), on the current stream."""
+        n = send.numel()
+        with torch.cuda.device(self.device):
+            if recv is None:
+                recv = torch.empty(self.comm_world * n, dtype=torch.float32, device=self.device)
+            self._check(self.lib.blim_allgather_scores(self.h, None, ctypes.c_void_p(send.data_ptr()), ctypes.c_void_p(recv.data_ptr()), n,
+                                                       self._stream()))
+        return recv
+
     # ---------------------------------------------------------------- fuse / rerank
     def fuse_rerank(self, cand_idx, cand, prior, query, iv2, alpha, c_query, c_ens, use_prior=True, use_query=True,
                     cpn_zero_f64=False, row0=0):

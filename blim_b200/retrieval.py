@@ -8,8 +8,8 @@ CUDA engine.
 Differences in HOW (not in WHAT): a row's top-k candidates are not pushed through per-row padded batches; all rows'
 (video, text) pairs go to Engine.score_pairs in one call, which shares video / text prefixes and never materialises the
 logits.  evaluation() additionally scores each distinct (video, text) pair once for both directions and shards the
-pairs by video over the ranks, combining them with one all-gather of compact scores instead of dense all-reduces
-(reference retrieval_utils.py:252-262).
+pairs by prefix owner over the ranks, combining them with ONE all-gather of compact scores (NCCL, enqueued by the engine
+on the compute stream) instead of dense all-reduces (reference retrieval_utils.py:252-262).
 """
 import datetime
 import time
@@ -131,28 +131,9 @@ class PairPlan:
         self.t2v_np = (packed[2 * nu + 2 * na:2 * nu + 2 * na + nb], packed[2 * nu + 2 * na + nb:])
 
 
-def balanced_owner_ranks(owner, pair_cost, owner_base_cost, world):
-    """Which rank scores which prefix owner: owners sorted by estimated decoder tokens (shared prefix once + the suffix
-    tokens of all their pairs), largest first, each to the currently lightest rank (LPT).  Deterministic, so every rank
-    derives the same assignment from the plan.  Returns rank_of_owner indexed by owner id."""
-    n_owner = int(owner.max()) + 1 if len(owner) else 0
-    cost = np.bincount(owner, weights=pair_cost, minlength=n_owner).astype(np.float64)
-    used = cost > 0
-    cost = cost + np.where(used, owner_base_cost, 0.0)
-    order = np.argsort(-cost, kind="stable")
-    load = np.zeros(world)
-    rank_of = np.zeros(n_owner, dtype=np.int64)
-    for o in order:
-        if not used[o]:
-            break
-        r = int(np.argmin(load))
-        rank_of[o] = r
-        load[r] += cost[o]
-    return rank_of
-
-
 def _shard_costs(eng, kind, pv, pt):
-    """(owner ids, per-pair suffix tokens, per-owner prefix tokens) for the scheduler's four run shapes (csrc/engine.cu)."""
+    """(owner type, owner ids, per-pair suffix tokens, per-owner prefix tokens) for the scheduler's four run shapes
+    (csrc/engine.cu).  Owner = the id whose shared prefix the pairs hang off: "v" (video) or "t" (text)."""
     lens = getattr(eng, "text_lens", None)
     if not lens or TEXTS_VTG not in lens or TEXTS_TVG not in lens:
         lens = None
@@ -160,55 +141,104 @@ def _shard_costs(eng, kind, pv, pt):
     cap = lens[TEXTS_VTG]["scored"] if lens else None
     tlen = lens[TEXTS_TVG]["total"] if lens else None
     if kind == VTG:          # owner = video: prefix (header + visual rows + prompt) once, one caption suffix per pair
-        return pv, (cap[pt] if lens else np.full(len(pv), 14.0)), n_vis + 26.0
+        return "v", pv, (cap[pt] if lens else np.full(len(pv), 14.0)), n_vis + 26.0
     if kind == VTG_PRIOR:    # owner = text: one suffix per distinct text, the 26-token prefix is shared by everyone
-        return pt, (cap[pt] / 16.0 if lens else np.ones(len(pt))), 0.0
+        return "t", pt, (cap[pt] / 16.0 if lens else np.ones(len(pt))), 0.0
     if kind == TVG:          # owner = text: text prefix once, n_clips - 1 visual rows per pair
-        return pt, np.full(len(pt), 3.0), (tlen if lens else 45.0)
-    return pv, np.full(len(pv), 4.0), 0.0   # TVG_PRIOR, owner = video
+        return "t", pt, np.full(len(pt), 3.0), (tlen if lens else 45.0)
+    return "v", pv, np.full(len(pv), 4.0), 0.0   # TVG_PRIOR, owner = video
+
+
+def balanced_owner_ranks(costs, world):
+    """Which rank scores which prefix owner.  `costs` = {"v": per-video decoder tokens, "t": per-text decoder tokens}
+    summed over ALL score kinds of the evaluation: videos and texts go into one list, largest first, each to the currently
+    lightest rank (LPT).  The ranks meet once, at the single all-gather, so only the total per rank matters.
+    Deterministic: every rank derives the same assignment from the plan.  Returns {"v": rank_of_video, "t": rank_of_text}."""
+    items = [(float(c), typ, i) for typ in ("v", "t") for i, c in enumerate(costs.get(typ, ())) if c > 0]
+    items.sort(key=lambda x: (-x[0], x[1], x[2]))
+    load = np.zeros(world)
+    rank_of = {typ: np.zeros(len(costs.get(typ, ())), dtype=np.int64) for typ in ("v", "t")}
+    for c, typ, i in items:
+        r = int(np.argmin(load))
+        rank_of[typ][i] = r
+        load[r] += c
+    return rank_of
+
+
+class ShardPlan:
+    """Who scores what, and where it lands: per score kind the pair indices of every rank, the offset of that shard in the
+    rank's send buffer (all kinds concatenated), and the gather indices that unpack the all-gathered buffer."""
+
+    def __init__(self, eng, jobs, world, n_videos, n_texts):
+        costs = {"v": np.zeros(n_videos), "t": np.zeros(n_texts)}
+        owners = {}
+        for name, kind, pv, pt in jobs:
+            typ, owner, pair_cost, base = _shard_costs(eng, kind, pv, pt)
+            n_owner = len(costs[typ])
+            c = np.bincount(owner, weights=pair_cost, minlength=n_owner).astype(np.float64)
+            base = base[:n_owner] if isinstance(base, np.ndarray) else base
+            costs[typ] += c + np.where(c > 0, base, 0.0)
+            owners[name] = (typ, owner)
+        rank_of = balanced_owner_ranks(costs, world)
+        self.shards = {}                      # name -> [pair indices of rank r]
+        fill = np.zeros(world, dtype=np.int64)
+        self.offsets = {}                     # name -> [offset of that shard in rank r's send buffer]
+        for name, kind, pv, pt in jobs:
+            typ, owner = owners[name]
+            pair_rank = rank_of[typ][owner]
+            self.shards[name] = [np.nonzero(pair_rank == r)[0] for r in range(world)]
+            self.offsets[name] = fill.copy()
+            fill += np.array([len(x) for x in self.shards[name]])
+        self.width = int(max(1, fill.max()))  # floats every rank contributes (padded to the longest)
+        self.world = world
+
+    def unpack_indices(self, name):
+        """(src positions in the gathered [world * width] buffer, dst positions in the kind's per-pair array)."""
+        src = np.concatenate([r * self.width + self.offsets[name][r] + np.arange(len(x)) for r, x in enumerate(self.shards[name])])
+        dst = np.concatenate(self.shards[name])
+        return src, dst
 
 
 def score_all(model, plan: PairPlan, cpn=True, full=True, distributed=False):
-    """Scores every term evaluation() needs on the deduplicated pair set.  Multi-GPU: the pairs are sharded by the id
-    that owns the shared prefix (each video / text prefix is prefilled on exactly one rank); every rank derives all
-    ranks' shards from the same plan, so the only communication is ONE all-gather of padded fp32 scores per score kind
-    (no index or size exchange, no host synchronisation).
+    """Scores every term evaluation() needs on the deduplicated pair set.  Multi-GPU: the pairs of all score kinds are
+    sharded by the id that owns the shared prefix (each video / text prefix is prefilled on exactly one rank), balanced
+    on the SUM of the kinds' decoder tokens; every rank derives all ranks' shards from the same plan, scores its own into
+    one send buffer, and the ranks meet ONCE: a single all-gather of padded fp32 scores (blim_allgather_scores, NCCL on
+    the compute stream; no index or size exchange, no host synchronisation) replaces the reference's barrier + 2-6 dense
+    all-reduces (retrieval_utils.py:252-262).
     Returns a dict of compact device tensors aligned with plan.union_* (vtg, tvg) / plan.v2t_pairs (vtg_prior) /
     plan.t2v_pairs (tvg_prior)."""
     m = _engine_model(model)
     eng = m.engine
     rank, world = _world() if distributed else (0, 1)
-
-    def run(kind, pv, pt):
-        if world == 1:
-            return eng.score_pairs(kind, pv, pt)
-        # shard by the id that owns the shared prefix (video for VTG / TVG prior, text for VTG prior / TVG), owners
-        # assigned to ranks by estimated decoder tokens so that the ranks finish together
-        owner, pair_cost, base = _shard_costs(eng, kind, pv, pt)
-        base = base[: int(owner.max()) + 1] if isinstance(base, np.ndarray) else base
-        rank_of = balanced_owner_ranks(owner, pair_cost, base, world)
-        pair_rank = rank_of[owner]
-        shards = [np.nonzero(pair_rank == r)[0] for r in range(world)]
-        width = max(len(x) for x in shards)
-        buf = torch.zeros(width, dtype=torch.float32, device=eng.device)
-        mine = shards[rank]
-        if len(mine):
-            eng.score_pairs(kind, pv[mine], pt[mine], out=buf[:len(mine)])
-        gathered = torch.empty(world * width, dtype=torch.float32, device=eng.device)
-        dist.all_gather_into_tensor(gathered, buf)
-        src = np.concatenate([r * width + np.arange(len(x)) for r, x in enumerate(shards)])
-        dst = np.concatenate(shards)
-        out = torch.empty(len(pv), dtype=torch.float32, device=eng.device)
-        out[torch.from_numpy(dst).to(eng.device, non_blocking=True)] = gathered[torch.from_numpy(src).to(eng.device, non_blocking=True)]
-        return out
-
-    out = {"vtg": run(VTG, *plan.union_np)}
+    jobs = [("vtg", VTG) + tuple(plan.union_np)]
     if cpn:
-        out["vtg_prior"] = run(VTG_PRIOR, *plan.v2t_np)
+        jobs.append(("vtg_prior", VTG_PRIOR) + tuple(plan.v2t_np))
     if full:
-        out["tvg"] = run(TVG, *plan.union_np)
+        jobs.append(("tvg", TVG) + tuple(plan.union_np))
         if cpn:
-            out["tvg_prior"] = run(TVG_PRIOR, *plan.t2v_np)
+            jobs.append(("tvg_prior", TVG_PRIOR) + tuple(plan.t2v_np))
+    if world == 1:
+        return {name: eng.score_pairs(kind, pv, pt) for name, kind, pv, pt in jobs}
+    sp = ShardPlan(eng, jobs, world, plan.n_videos, plan.n_texts)
+    send = torch.zeros(sp.width, dtype=torch.float32, device=eng.device)
+    for name, kind, pv, pt in jobs:
+        mine = sp.shards[name][rank]
+        if len(mine):
+            off = int(sp.offsets[name][rank])
+            eng.score_pairs(kind, pv[mine], pt[mine], out=send[off:off + len(mine)])
+    if hasattr(eng, "allgather_scores"):
+        eng.comm_init()                        # first call only: joins the engine's NCCL communicator
+        gathered = eng.allgather_scores(send)
+    else:                                      # host-logic tests on CPU (gloo) with a stand-in engine
+        gathered = torch.empty(world * sp.width, dtype=torch.float32, device=eng.device)
+        dist.all_gather_into_tensor(gathered, send)
+    out = {}
+    for name, kind, pv, pt in jobs:
+        src, dst = sp.unpack_indices(name)
+        res = torch.empty(len(pv), dtype=torch.float32, device=eng.device)
+        res[torch.from_numpy(dst).to(eng.device, non_blocking=True)] = gathered[torch.from_numpy(src).to(eng.device, non_blocking=True)]
+        out[name] = res
     return out
 
 

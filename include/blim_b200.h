@@ -146,6 +146,19 @@ int blim_profile_read(blim_engine* e, double* gemm_ms, double* attn_ms, int64_t*
  * of the GEMM launches (0 for attention / RMSNorm). */
 int blim_profile_read_detail(blim_engine* e, int n, double* ms, double* flops, int64_t* launches);
 
+/* ---- Multi-GPU exchange (one process / engine per GPU).  Replaces the reference's dist.barrier() + 2-6 dense N x N
+ * all_reduce(SUM) of -100-filled matrices (retrieval_utils.py:252-262) by ONE all-gather of compact per-pair scores.
+ * NCCL is resolved at run time (dlopen: the copy already in the process, $BLIM_NCCL_LIB, or the linker path).
+ *   blim_comm_unique_id : rank 0 creates the 128-byte ncclUniqueId; the caller distributes it (any channel).
+ *   blim_comm_init      : every rank joins (ncclCommInitRank on the engine's device); collective, call on all ranks.
+ *   blim_allgather_scores: recv[r*count .. (r+1)*count) = rank r's send[0 .. count), fp32 device buffers, enqueued on
+ *                         `stream` (the compute stream: no host synchronisation between scoring and rerank).
+ *                         nccl_comm = an ncclComm_t of the caller, or NULL for the engine's own communicator. */
+int blim_comm_unique_id(void* id_out128);
+int blim_comm_init(blim_engine* e, const void* id128, int rank, int world);
+int blim_comm_destroy(blim_engine* e);
+int blim_allgather_scores(blim_engine* e, void* nccl_comm, const float* send_dev, float* recv_dev, int64_t count_per_rank, void* stream);
+
 /* 16-bit format of the engine's tensor-core operands (weights as stored after blim_load_weight, activations), in
  * blim_load_weight's dtype codes: 2 = fp16 (default build), 1 = bf16 (-DBLIM_ACT_BF16); see csrc/act_type.cuh.  Only the
  * debug entries below expose operand-format buffers; every other entry point speaks the dtypes documented with it. */

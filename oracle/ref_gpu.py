@@ -44,7 +44,7 @@ class ReferenceRunner:
         self.autocast = autocast and dtype != torch.float32
         sd = {k: v.to(dtype) for k, v in state_dict.items()} if dtype != torch.bfloat16 else state_dict
         self.model, (self.ru, self.tu, self.mvf) = ref_harness.build_reference_model(
-            cfg, sd, dtype=dtype, image_token_id=cfg.image_token_id, device=self.device if self.device.type == "cuda" else None)
+            cfg, sd, dtype=dtype, image_token_id=cfg.image_token_id, device=self.device)
         del sd
         self.model.module.set_tvg_prefix_length(corpus.tvg_prefix_length)          # retrieval_utils.py:210
         self.video = [v.to(dtype) for v in corpus.video.cpu()]                     # the loader hands out CPU tensors (ru:55)

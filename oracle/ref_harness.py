@@ -96,6 +96,24 @@ def import_reference():
     return retrieval_utils, training_utils, mvf
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def _skip_random_init():
+    """Parameters are overwritten by load_state_dict right after construction: skip the constructors' random fills (minutes
+    for 7.6 G parameters on host cores)."""
+    names = ("kaiming_uniform_", "uniform_", "normal_", "trunc_normal_", "xavier_uniform_", "zeros_", "ones_", "constant_")
+    saved = {n: getattr(torch.nn.init, n) for n in names}
+    try:
+        for n in names:
+            setattr(torch.nn.init, n, lambda t, *a, **k: t)
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(torch.nn.init, n, f)
+
+
 class _Wrap(torch.nn.Module):
     """evaluation()/compute_*_scores_x expect a DDP-like object with `.module` (retrieval_utils.py:66)."""
 
@@ -136,14 +154,21 @@ def build_reference_model(cfg, state_dict, dtype=torch.float32, image_token_id=N
     else:
         old = torch.get_default_dtype()
         torch.set_default_dtype(dtype)
+        saved_init = mvf.VideoChatFlashQwenForCausalLM._init_weights
+        mvf.VideoChatFlashQwenForCausalLM._init_weights = lambda self, module: None
         try:
-            with torch.device(device):
+            with torch.device(device), _skip_random_init():
                 model = mvf.VideoChatFlashQwenForCausalLM(c)
         finally:
             torch.set_default_dtype(old)
+            mvf.VideoChatFlashQwenForCausalLM._init_weights = saved_init
     missing, unexpected = model.load_state_dict(state_dict, strict=False)
     need = [k for k in missing if not k.startswith("model.vision_tower") and "rotary_emb" not in k]
     assert not need, f"reference parameters not provided: {need[:5]}"
+    if device is not None:   # nothing may be left at its (skipped) initial value
+        loaded = set(state_dict)
+        left = [k for k, _ in model.named_parameters() if k not in loaded and not k.startswith("model.vision_tower")]
+        assert not left, f"reference parameters left uninitialised: {left[:5]}"
     model = model.to(dtype).eval()
     if image_token_id is not None:
         ru.IMAGE_TOKEN_ID = image_token_id  # small vocabularies: remap the module attribute (retrieval_utils.py:14,99)

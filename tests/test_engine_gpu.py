@@ -77,18 +77,22 @@ def test_sharded_scores_are_bit_identical(golden_case):
     name, spec, cfg, weights, corpus, eng, gold = golden_case
     ref = gold["v2t_vtg_lik"]
     rows, cols = np.nonzero(ref != -100.0)
-    for kind in (VTG, VTG_PRIOR, TVG, TVG_PRIOR):
-        full = eng.score_pairs(kind, rows, cols).cpu().numpy()
-        owner, cost, base = retrieval._shard_costs(eng, kind, rows, cols)
-        base = base[: int(owner.max()) + 1] if isinstance(base, np.ndarray) else base
-        for world in (2, 3, 8):
-            for rank_of in (np.arange(int(owner.max()) + 1) % world, retrieval.balanced_owner_ranks(owner, cost, base, world)):
-                got = np.empty_like(full)
+    jobs = [("vtg", VTG, rows, cols), ("vtg_prior", VTG_PRIOR, rows, cols), ("tvg", TVG, rows, cols), ("tvg_prior", TVG_PRIOR, rows, cols)]
+    full = {name: eng.score_pairs(kind, pv, pt).cpu().numpy() for name, kind, pv, pt in jobs}
+    for world in (2, 3, 8):
+        sp = retrieval.ShardPlan(eng, jobs, world, corpus.n, corpus.n)     # owners balanced on the summed cost of the four kinds
+        strided = {name: [np.nonzero((pv if kind in (VTG, TVG_PRIOR) else pt) % world == r)[0] for r in range(world)] for name, kind, pv, pt in jobs}
+        for shards in (sp.shards, strided):
+            for name, kind, pv, pt in jobs:
+                got = np.empty_like(full[name])
+                seen = np.zeros(len(pv), dtype=int)
                 for r in range(world):
-                    mine = np.nonzero(rank_of[owner] == r)[0]
+                    mine = shards[name][r]
+                    seen[mine] += 1
                     if len(mine):
-                        got[mine] = eng.score_pairs(kind, rows[mine], cols[mine]).cpu().numpy()
-                assert np.array_equal(got, full), (kind, world, np.abs(got - full).max())
+                        got[mine] = eng.score_pairs(kind, pv[mine], pt[mine]).cpu().numpy()
+                assert (seen == 1).all()
+                assert np.array_equal(got, full[name]), (name, world, np.abs(got - full[name]).max())
 
 
 def _mid_cfg():

@@ -154,20 +154,49 @@ def test_committed_ncu_launch_list_reproduces_the_share_summary(tmp_path):
 
 
 def test_balanced_owner_ranks_lpt():
-    """Multi-GPU sharding: every owner on exactly one rank, loads within one largest item of each other, deterministic."""
+    """Multi-GPU sharding: videos and texts are balanced TOGETHER on their summed decoder tokens; every owner on exactly one
+    rank, rank loads within one largest item of each other, deterministic."""
     from blim_b200.retrieval import balanced_owner_ranks
     rng = np.random.default_rng(0)
-    owner = rng.integers(0, 200, size=3000)
-    owner = owner[owner % 7 != 3]                      # some owner ids never occur
-    cost = rng.integers(3, 40, size=len(owner)).astype(np.float64)
+    costs = {"v": rng.integers(0, 900, size=200).astype(np.float64), "t": rng.integers(0, 120, size=300).astype(np.float64)}
+    costs["v"][::7] = 0.0                               # some owners have nothing to score
     for world in (2, 3, 8):
-        rank_of = balanced_owner_ranks(owner, cost, 282.0, world)
-        assert np.array_equal(rank_of, balanced_owner_ranks(owner, cost, 282.0, world))
-        per_owner = np.bincount(owner, weights=cost, minlength=len(rank_of)) + np.where(np.bincount(owner, minlength=len(rank_of)) > 0, 282.0, 0.0)
-        load = np.bincount(rank_of, weights=per_owner, minlength=world)
-        assert load.max() - load.min() <= per_owner.max()
-        naive = np.bincount(np.arange(len(rank_of)) % world, weights=per_owner, minlength=world)
+        rank_of = balanced_owner_ranks(costs, world)
+        again = balanced_owner_ranks(costs, world)
+        assert all(np.array_equal(rank_of[k], again[k]) for k in rank_of)
+        load = sum(np.bincount(rank_of[k], weights=costs[k], minlength=world) for k in ("v", "t"))
+        assert load.max() - load.min() <= max(costs["v"].max(), costs["t"].max())
+        naive = sum(np.bincount(np.arange(len(costs[k])) % world, weights=costs[k], minlength=world) for k in ("v", "t"))
         assert load.max() <= naive.max() + 1e-9          # never worse than the round-robin it replaces
+
+
+def test_shard_plan_layout():
+    """One send buffer per rank holds all score kinds back to back; the unpack indices are a bijection onto every kind's pairs."""
+    from blim_b200.retrieval import PairPlan, ShardPlan
+    from blim_b200.engine import TVG, TVG_PRIOR, VTG, VTG_PRIOR
+    g = torch.Generator().manual_seed(3)
+    t2v = torch.randn(40, 40, generator=g) + 3 * torch.eye(40)
+    plan = PairPlan(t2v.t().contiguous(), t2v, 6, "cpu")
+    jobs = [("vtg", VTG) + tuple(plan.union_np), ("vtg_prior", VTG_PRIOR) + tuple(plan.v2t_np), ("tvg", TVG) + tuple(plan.union_np),
+            ("tvg_prior", TVG_PRIOR) + tuple(plan.t2v_np)]
+    for world in (2, 5):
+        sp = ShardPlan(_FakeEngine(), jobs, world, 40, 40)
+        used = np.zeros(world * sp.width, dtype=int)
+        for name, kind, pv, pt in jobs:
+            src, dst = sp.unpack_indices(name)
+            assert sorted(dst.tolist()) == list(range(len(pv)))
+            used[src] += 1
+            for r in range(world):        # a rank's shard of a kind is contiguous in its send buffer
+                lo = r * sp.width + sp.offsets[name][r]
+                assert np.array_equal(np.sort(src[np.isin(dst, sp.shards[name][r])]), np.arange(lo, lo + len(sp.shards[name][r])))
+        assert used.max() == 1             # no two scores share a slot
+        owner_rank = {}
+        for name, kind, pv, pt in jobs:    # a video's VTG pairs and its TVG-prior pairs live on the same rank (one upload, one prefix)
+            own = pv if kind in (VTG, TVG_PRIOR) else pt
+            typ = "v" if kind in (VTG, TVG_PRIOR) else "t"
+            for r in range(world):
+                for o in np.unique(own[sp.shards[name][r]]):
+                    assert owner_rank.setdefault((typ, int(o)), r) == r
 
 
 def test_algorithmic_flops_matches_survey_order_of_magnitude():

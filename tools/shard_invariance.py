@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """How much do per-pair scores depend on how the pair set is sharded?  One GPU emulates the W ranks of a multi-GPU run
-(retrieval.balanced_owner_ranks) and compares every score kind with the unsharded run.  Prints max |d| and how many scores
+(retrieval.ShardPlan) and compares every score kind with the unsharded run.  Prints max |d| and how many scores
 differ at all.  (Different shards batch different sequences into one attention tile, so own-key chunk boundaries and the
 lazy-rescale history differ: last-bit differences before a bf16 rounding, never more than rounding noise.)
 
@@ -39,15 +39,14 @@ def main():
     eng.set_video_vocab(corpus.video_vocab, corpus.tvg_video_labels.numpy())
     model.set_tvg_prefix_length(corpus.tvg_prefix_length)
     plan = retrieval.PairPlan(corpus.v2t_iv2.to(dev), corpus.t2v_iv2.to(dev), 16, dev, engine=eng)
-    for kind, (pv, pt), label in ((VTG, plan.union_np, "vtg"), (VTG_PRIOR, plan.v2t_np, "vtg_prior"), (TVG, plan.union_np, "tvg"),
-                                  (TVG_PRIOR, plan.t2v_np, "tvg_prior")):
+    jobs = [("vtg", VTG) + tuple(plan.union_np), ("vtg_prior", VTG_PRIOR) + tuple(plan.v2t_np), ("tvg", TVG) + tuple(plan.union_np),
+            ("tvg_prior", TVG_PRIOR) + tuple(plan.t2v_np)]
+    sp = retrieval.ShardPlan(eng, jobs, args.world, plan.n_videos, plan.n_texts)
+    for label, kind, pv, pt in jobs:
         full = eng.score_pairs(kind, pv, pt).cpu().numpy()
-        owner, cost, base = retrieval._shard_costs(eng, kind, pv, pt)
-        base = base[: int(owner.max()) + 1] if isinstance(base, np.ndarray) else base
-        rank_of = retrieval.balanced_owner_ranks(owner, cost, base, args.world)
         got = np.empty_like(full)
         for r in range(args.world):
-            mine = np.nonzero(rank_of[owner] == r)[0]
+            mine = sp.shards[label][r]
             if len(mine):
                 got[mine] = eng.score_pairs(kind, pv[mine], pt[mine]).cpu().numpy()
         d = np.abs(got - full)
