@@ -59,7 +59,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2",
+                    help="one of %s, 'extract' (feature-extractor bench, tools/extract_bench.py), or a comma list with optional top-k "
+                         "overrides sharing one engine / one weight load, e.g. c3,c5@16,c5@32,c5@64,c4 (one JSON line each)" % sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the number of queries/videos (debug)")
     ap.add_argument("--topk", type=int, default=0, help="override the workload's top-k")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -363,28 +365,42 @@ def parity_with_reference(cfg, eng, corpus, plan, topk, alpha, c, dev, t2v_iv2, 
 
 def main():
     args = parse()
-    wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "extract":     # the step before the path: its own bench, same JSON contract
+        if rank == 0:
+            sys.argv = [sys.argv[0], "--steps", str(max(args.steps, 1)), "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import extract_bench
+            extract_bench.main()
+        return
+    specs = []
+    for item in args.workload.split(","):
+        name, _, k = item.partition("@")
+        if name not in WORKLOADS:
+            raise SystemExit(f"bench.py: unknown workload {name!r} (choose from {sorted(WORKLOADS)} or 'extract')")
+        specs.append((WORKLOADS[name], int(k) if k else 0))
     if args.impl == "reference":
-        run_reference_arm(args, wl, rank, world)
+        run_reference_arm(args, specs[0][0], rank, world)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the BLiM B200 engine has no CPU fallback")
+    if len({wl["model"] for wl, _ in specs}) != 1:
+        raise SystemExit("bench.py: the workloads of one run must share the model")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from blim_b200 import evalloop, retrieval, synth
+    from blim_b200 import synth
     from blim_b200.engine import ModelConfig
     from blim_b200.model import BlimModel
 
-    cfg = ModelConfig.qwen2_7b() if wl["model"] == "qwen2_7b" else ModelConfig.tiny()
+    wl0 = specs[0][0]
+    cfg = ModelConfig.qwen2_7b() if wl0["model"] == "qwen2_7b" else ModelConfig.tiny()
     dev = torch.device("cuda", local_rank)
     model = BlimModel(cfg, device=local_rank, gemm_cta_group=args.cta_group, max_run_tokens=args.run_tokens, max_prefix_tokens=args.run_tokens)
     eng = model.engine
     want_cpu = (not args.no_cpu_baseline) and rank == 0 and world == 1
-    want_parity = (not args.no_parity) and rank == 0 and world == 1 and wl["model"] == "qwen2_7b"
     weights_cpu = {}
     shapes = synth.param_shapes(cfg)
     # stream the random-init parameters through the engine one tensor at a time (same seeds on every rank)
@@ -395,8 +411,22 @@ def main():
             weights_cpu[name] = t.cpu()
         del t
     eng.set_rope(torch.float32)
+    for i, (wl, k) in enumerate(specs):
+        last = i == len(specs) - 1
+        run_workload(args, wl, k or args.topk, cfg, model, dev, rank, world, local_rank, weights_cpu if (want_cpu and last) else None)
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_workload(args, wl, topk_override, cfg, model, dev, rank, world, local_rank, weights_cpu):
+    """One workload on an engine whose weights are already loaded: device-resident steps, e2e steps, checks, one JSON line."""
+    from blim_b200 import evalloop, retrieval, synth
+    eng = model.engine
+    want_cpu = weights_cpu is not None
+    want_parity = (not args.no_parity) and rank == 0 and world == 1 and wl["model"] == "qwen2_7b"
     corpus = synth.make_corpus(cfg, wl["dataset"], n=args.n or wl["n"], n_clips=wl["n_clips"], seed=1, feat_device=dev)
-    n, topk = corpus.n, (args.topk or wl["topk"])
+    n, topk = corpus.n, (topk_override or wl["topk"])
     alpha, c = wl["alpha"], wl["c"]
 
     # device-resident inputs for `value`
@@ -477,7 +507,10 @@ def main():
 
     # end to end through the reference-facing API with HOST inputs (pinned), copies inside the timed region
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and corpus.video.numel() * 2 > (4 << 30):
+        e2e = {"value": None, "unit": UNIT, "skipped": f"{corpus.video.numel() * 2 / 2**30:.1f} GB of features per rank: the pinned host copy of every rank "
+                                                        "does not fit this bench's host budget; measured device-resident only"}
+    elif not args.no_e2e:
         loader = Loader(corpus, pin=True)
         host_scores = {"v2t": corpus.v2t_iv2.cpu().pin_memory(), "t2v": corpus.t2v_iv2.cpu().pin_memory()}
         eargs = argparse.Namespace(topk=topk, batch_size_eval=16, num_clips=corpus.n_clips, cpn=True, eval=True, resume="synthetic",
@@ -528,8 +561,6 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "rank_parity": rank_parity, "reference_gpu": reference_gpu, "recall_blim": res}
         print(json.dumps(line), flush=True)
-    if distributed:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -159,6 +159,8 @@ struct blim_engine {
   DevBuf io_in, io_out;      // bf16 <-> activation-format staging of the compat entry points (allocated on first use)
   DevBuf vis_in, d_vis_idx;  // projector input staging for non-contiguous video sets (gathered feature rows + their indices)
   DevBuf d_tok_slot, d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
+  int ksplit = 1, nsplit = 0;             // K slices of the long-K residual GEMM (1 = off) / N slices of gate|up (0 = by weight size)
+  size_t ksplit_min_bytes = 100u << 20;   // weights larger than this are K-sliced
   int attn_version = kAttnPersistent;  // BLIM_ATTN=tc2 selects the per-item kernel (A/B against the persistent default)
   uint8_t* arena = nullptr;  // pinned staging arena for scheduler metadata (see upload())
   size_t arena_cap = 0, arena_off = 0;
@@ -228,8 +230,8 @@ template <class Epi> struct EpiProf { static int sub(const blim_engine*, int) { 
 template <int D> struct EpiProf<EpiQkvRope<D>> { static int sub(const blim_engine*, int) { return kProfQkv; } };
 template <> struct EpiProf<EpiSwiglu> { static int sub(const blim_engine*, int) { return kProfGateUp; } };
 template <> struct EpiProf<EpiLse> { static int sub(const blim_engine*, int) { return kProfLse; } };
-template <int G> struct EpiProf<EpiResidT<G>> { static int sub(const blim_engine* e, int K) { return K == e->I ? kProfDown : kProfOProj; } };
-template <> struct EpiProf<EpiResidNorm> { static int sub(const blim_engine* e, int K) { return K == e->I ? kProfDown : kProfOProj; } };
+template <int G> struct EpiProf<EpiResidT<G>> { static int sub(const blim_engine* e, int K) { return K == e->NQ ? kProfOProj : kProfDown; } };   // down_proj may be K-sliced
+template <> struct EpiProf<EpiResidNorm> { static int sub(const blim_engine* e, int K) { return K == e->NQ ? kProfOProj : kProfDown; } };
 
 template <class Epi>
 // A = activation operand, W = weight operand, both in the operand format act_t.
@@ -315,6 +317,8 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
     e->fuse_norm = f && std::string(f) == "1";
   }
   e->gemm.cta_group = cfg->gemm_cta_group == 1 ? 1 : 2;  // default: CTA pairs (cta_group::2)
+  if (const char* v = getenv("BLIM_GEMM_KSPLIT")) e->ksplit = std::max(1, std::min(8, atoi(v)));
+  if (const char* v = getenv("BLIM_GEMM_NSPLIT")) e->nsplit = std::max(1, std::min(16, atoi(v)));
   if (const char* h = getenv("BLIM_GEMM_HINTS")) e->gemm.l2_hints = atoi(h) != 0;
   if (const char* m = getenv("BLIM_GEMM_SB_MB")) { e->gemm.sb_mb = std::max(4, std::min(96, atoi(m))); e->gemm.sb_auto = false; }
   if (const char* m = getenv("BLIM_GEMM_SB_MIN")) { e->gemm.sb_min = std::max(1, std::min(8, atoi(m))); e->gemm.sb_auto = false; }
@@ -722,7 +726,36 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
       return 0;
     }
     EpiResid::Params pr{x, e->H};
-    return gemm<EpiResid>(e, A, lda, W, lda, R, e->H, K, pr, st);
+    // A/B knob (BLIM_GEMM_KSPLIT, default 1 = off): cut a long-K contraction (down_proj, 136 MB of weights) into K slices,
+    // one launch each -- the epilogue accumulates into x anyway.  Measured: DRAM reads per launch at
+    // M = 25 728 drop from 8.7 GB to 6.4 GB (2 slices), but the 68 MB slices still do not stay L2-resident and every slice
+    // pays the fp32 read-modify-write of x again: -1 % pairs/s on the same box with 2 or 3 slices, so it stays off.
+    int splits = 1;
+    if (R >= 2048 && static_cast<size_t>(e->H) * K * 2 > e->ksplit_min_bytes) splits = e->ksplit;
+    const int kb = K / kBK;
+    for (int i = 0; i < splits; ++i) {
+      const int k0 = (kb * i / splits) * kBK, k1 = (kb * (i + 1) / splits) * kBK;
+      if (k1 > k0) CKR(gemm<EpiResid>(e, A + k0, lda, W + k0, lda, R, e->H, k1 - k0, pr, st));
+    }
+    return 0;
+  };
+  // gate|up: 271 MB of weights against a 126 MB L2 whose two halves each cache what their own SMs touch.  One launch
+  // per N slice of <= 46 MB (6 at 7B): the slice stays L2-resident while the A panels stream through once per slice (m-tile
+  // by m-tile, n fastest), instead of the whole weight streaming once per 40 MB super-block of A.  ncu at M = 25 728: DRAM
+  // reads 5.8 GB -> 2.3 GB per layer, writes unchanged; same box: +1.1 % pairs/s (the saved DRAM power goes to the SM
+  // clock: 1 275 -> 1 305 MHz under the cap).  BLIM_GEMM_NSPLIT overrides (1 = one launch).
+  auto swiglu_gemm = [&](const act_t* A, const act_t* W, act_t* act, int R) -> int {
+    const int n_tiles = (2 * e->I + kBN - 1) / kBN;
+    const int want = e->nsplit > 0 ? e->nsplit : static_cast<int>((2 * static_cast<size_t>(e->I) * e->H * 2 + (46u << 20) - 1) / (46u << 20));
+    const int splits = (R >= 2048) ? std::max(1, std::min(want, n_tiles)) : 1;
+    for (int i = 0; i < splits; ++i) {
+      const int t0 = n_tiles * i / splits, t1 = n_tiles * (i + 1) / splits;
+      if (t1 <= t0) continue;
+      const int n0 = t0 * kBN, n1 = std::min(t1 * kBN, 2 * e->I);
+      EpiSwiglu::Params ps{act + static_cast<size_t>(t0) * (kBN / 2), e->I, rstd};
+      CKR(gemm<EpiSwiglu>(e, A, e->H, W + static_cast<size_t>(n0) * e->H, e->H, R, n1 - n0, e->H, ps, st));
+    }
+    return 0;
   };
   if (fuse) CKR(rowprep(e->x.as<float>(), T));
   for (int l = 0; l < e->NL; ++l) {
@@ -767,15 +800,13 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
       CKR(resid_gemm(e->xn.as<act_t>(), e->NQ, w.w_o.as<act_t>(), e->NQ, e->prefix_last.as<float>(), U, false));
       if (fuse) CKR(rowprep(e->prefix_last.as<float>(), U));
       else CKR(rmsnorm(e, e->xn.as<act_t>(), e->prefix_last.as<float>(), nullptr, nullptr, w.ln2.as<float>(), U, st));
-      EpiSwiglu::Params psl{e->act.as<act_t>(), e->I, rstd};
-      CKR(gemm<EpiSwiglu>(e, e->xn.as<act_t>(), e->H, w.w_gu.as<act_t>(), e->H, U, 2 * e->I, e->H, psl, st));
+      CKR(swiglu_gemm(e->xn.as<act_t>(), w.w_gu.as<act_t>(), e->act.as<act_t>(), U));
       CKR(resid_gemm(e->act.as<act_t>(), e->I, w.w_down.as<act_t>(), e->I, e->prefix_last.as<float>(), U, false));
       break;
     }
     CKR(resid_gemm(e->attn.as<act_t>(), e->NQ, w.w_o.as<act_t>(), e->NQ, e->x.as<float>(), T, fuse));
     if (!fuse) CKR(rmsnorm(e, e->xn.as<act_t>(), e->x.as<float>(), nullptr, nullptr, w.ln2.as<float>(), T, st));
-    EpiSwiglu::Params ps{e->act.as<act_t>(), e->I, rstd};
-    CKR(gemm<EpiSwiglu>(e, e->xn.as<act_t>(), e->H, w.w_gu.as<act_t>(), e->H, T, 2 * e->I, e->H, ps, st));
+    CKR(swiglu_gemm(e->xn.as<act_t>(), w.w_gu.as<act_t>(), e->act.as<act_t>(), T));
     CKR(resid_gemm(e->act.as<act_t>(), e->I, w.w_down.as<act_t>(), e->I, e->x.as<float>(), T, fuse && l + 1 < e->NL));
   }
   return 0;

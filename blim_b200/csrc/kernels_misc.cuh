@@ -55,8 +55,8 @@ __global__ void bf16_rows_to_f32_kernel(float* __restrict__ x, const __nv_bfloat
 // dtype, then multiplied by the (model dtype) weight.  Here the product is formed in fp32 and rounded ONCE to the
 // activation format (the reference's intermediate cast only adds a rounding).  Row gather: row r reads
 // x0[idx[r]] when idx[r] >= 0 else x1[-1 - idx[r]] (idx == nullptr -> identity on x0).
-__global__ void rmsnorm_kernel(act_t* __restrict__ out, const float* __restrict__ x0, const float* __restrict__ x1,
-                               const int* __restrict__ idx, const float* __restrict__ weight, int R, int H, float eps) {
+__global__ void __launch_bounds__(256) rmsnorm_kernel(act_t* __restrict__ out, const float* __restrict__ x0, const float* __restrict__ x1,
+                                                      const int* __restrict__ idx, const float* __restrict__ weight, int R, int H, float eps) {
   const int r = blockIdx.x;
   if (r >= R) return;
   const float* src;
@@ -66,30 +66,57 @@ __global__ void rmsnorm_kernel(act_t* __restrict__ out, const float* __restrict_
   } else {
     src = x0 + static_cast<size_t>(r) * H;
   }
+  // The row stays in registers between the two passes (up to 4 float4 per thread = H <= 4096 with 256 threads; all four
+  // loads are issued before the first use, so a block has its whole 14 KB row in flight at once); wider rows re-read it.
+  constexpr int kVec = 4;
+  const int n_vec = H >> 2;
+  const bool in_regs = n_vec <= kVec * 256;
+  float4 v[kVec];
   float ss = 0.f;
-  for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(src + c);
-    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  if (in_regs) {
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) {
+      const int c = threadIdx.x + k * 256;
+      v[k] = c < n_vec ? __ldcs(reinterpret_cast<const float4*>(src) + c) : make_float4(0.f, 0.f, 0.f, 0.f);   // read once: streaming
+    }
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) ss += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+  } else {
+    for (int c = threadIdx.x; c < n_vec; c += 256) {
+      const float4 t = reinterpret_cast<const float4*>(src)[c];
+      ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+    }
   }
-  __shared__ float red[32];
+  __shared__ float red[8];
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) red[0] = v;
-  }
-  __syncthreads();
-  const float rstd = rsqrtf(red[0] / static_cast<float>(H) + eps);
+  float tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot += red[k];      // same order in every thread: one barrier, deterministic
+  const float rstd = rsqrtf(tot / static_cast<float>(H) + eps);
   act_t* dst = out + static_cast<size_t>(r) * H;
-  for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(src + c);
-    const float4 w = *reinterpret_cast<const float4*>(weight + c);
-    uint2 u;
-    u.x = Fmt16<act_t>::pack2((v.x * rstd) * w.x, (v.y * rstd) * w.y);
-    u.y = Fmt16<act_t>::pack2((v.z * rstd) * w.z, (v.w * rstd) * w.w);
-    *reinterpret_cast<uint2*>(dst + c) = u;
+  if (in_regs) {
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) {
+      const int c = threadIdx.x + k * 256;
+      if (c < n_vec) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(weight) + c);
+        uint2 u;
+        u.x = Fmt16<act_t>::pack2((v[k].x * rstd) * w.x, (v[k].y * rstd) * w.y);
+        u.y = Fmt16<act_t>::pack2((v[k].z * rstd) * w.z, (v[k].w * rstd) * w.w);
+        reinterpret_cast<uint2*>(dst)[c] = u;
+      }
+    }
+  } else {
+    for (int c = threadIdx.x; c < n_vec; c += 256) {
+      const float4 t = reinterpret_cast<const float4*>(src)[c];
+      const float4 w = __ldg(reinterpret_cast<const float4*>(weight) + c);
+      uint2 u;
+      u.x = Fmt16<act_t>::pack2((t.x * rstd) * w.x, (t.y * rstd) * w.y);
+      u.y = Fmt16<act_t>::pack2((t.z * rstd) * w.z, (t.w * rstd) * w.w);
+      reinterpret_cast<uint2*>(dst)[c] = u;
+    }
   }
 }
 
