@@ -1048,7 +1048,7 @@ struct AttnTcMaps {
   CUtensorMap ka, va, kb, vb;
 };
 
-enum : int { kAttnPersistent = 5, kAttnPerItem = 2, kAttnIssueWarp = 4 };   // attention_tc2p / _tc2 / _tc4
+enum : int { kAttnPersistent = 5, kAttnPerItem = 2, kAttnIssueWarp = 4, kAttnWarpSpecialized = 6 };   // attention_tc2p / _tc2 / _tc4 / _tc5 (attention_ws.cuh)
 
 // cudaFuncSetAttribute once per (kernel instantiation, device): function attributes are per device
 template <class Kern>

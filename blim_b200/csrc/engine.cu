@@ -26,6 +26,7 @@
 #include "../../include/blim_b200.h"
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "attention_ws.cuh"
 #include "comm.cuh"
 #include "gemm_sm100.cuh"
 #include "kernels_misc.cuh"
@@ -161,7 +162,8 @@ struct blim_engine {
   DevBuf d_tok_slot, d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
   int ksplit = 1, nsplit = 0;             // K slices of the long-K residual GEMM (1 = off) / N slices of gate|up (0 = by weight size)
   size_t ksplit_min_bytes = 100u << 20;   // weights larger than this are K-sliced
-  int attn_version = kAttnPersistent;  // BLIM_ATTN=tc2 selects the per-item kernel (A/B against the persistent default)
+  int attn_version = kAttnWarpSpecialized;  // BLIM_ATTN=tc2p|tc2: the round-1 kernels (A/B against the warp-specialised default)
+  CUtensorMap tm_q;                          // e->q as a (head_dim, head, token) tensor: Q tiles by TMA (attention_ws.cuh)
   uint8_t* arena = nullptr;  // pinned staging arena for scheduler metadata (see upload())
   size_t arena_cap = 0, arena_off = 0;
   bool arena_disabled = false;
@@ -310,7 +312,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
   e->gemm.device = device;
   {
     const char* a = getenv("BLIM_ATTN");
-    e->attn_version = (a && std::string(a) == "tc2") ? kAttnPerItem : kAttnPersistent;
+    e->attn_version = (a && std::string(a) == "tc2") ? kAttnPerItem : (a && std::string(a) == "tc2p") ? kAttnPersistent : kAttnWarpSpecialized;
     const char* rs = getenv("BLIM_ROOT");
     e->root_share = !(rs && std::string(rs) == "0");
     const char* f = getenv("BLIM_FUSE_NORM");
@@ -329,6 +331,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
   };
   if (e->DH != 64 && e->DH != 128) return bad("head_dim must be 64 or 128");
   if (e->NKV <= 0 || e->NH % e->NKV) return bad("num_heads must be a multiple of num_kv_heads");
+  if (e->G > 128) return bad("more than 128 query heads per KV head");
   if (e->H % 64 || e->NQ % 64 || e->I % 128 || e->MM % 64) return bad("hidden/intermediate/mm sizes must be multiples of 64/128/64");
   if (e->H % 8 || e->NQ != e->H) return bad("num_heads*head_dim must equal hidden_size");
   if (kBN % e->DH) return bad("head_dim must divide 256");
@@ -357,7 +360,8 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
   cudaMemset(e->kp.p, 0, e->kp.cap); cudaMemset(e->vp.p, 0, e->vp.cap);
   cudaMemset(e->k_own.p, 0, e->k_own.cap); cudaMemset(e->v_own.p, 0, e->v_own.cap);
   if (!make_kv_tmap(&e->tm_kp, e->kp.p, static_cast<uint64_t>(e->NL) * P, e->NKVD) || !make_kv_tmap(&e->tm_vp, e->vp.p, static_cast<uint64_t>(e->NL) * P, e->NKVD) ||
-      !make_kv_tmap(&e->tm_kown, e->k_own.p, T, e->NKVD) || !make_kv_tmap(&e->tm_vown, e->v_own.p, T, e->NKVD)) {
+      !make_kv_tmap(&e->tm_kown, e->k_own.p, T, e->NKVD) || !make_kv_tmap(&e->tm_vown, e->v_own.p, T, e->NKVD) ||
+      !make_q_tmap(&e->tm_q, e->q.p, T, e->NH, e->DH, e->G, 128 / std::max(1, std::min(e->G, 128)))) {
     g_create_error = "cuTensorMapEncodeTiled failed for the K/V buffers";
     blim_destroy(e);
     return 1;
@@ -783,7 +787,8 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
       ap.key_valid = run.any_invalid ? e->d_key_valid.as<uint8_t>() : nullptr;
       ap.tok_seq_start = e->d_seq_start.as<int>(); ap.works = e->d_works.as<AttnWorkTc>();
       ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G; ap.scale_log2 = scale_log2; ap.q_stride = e->NQ; ap.n_works = n_works; ap.n_kv_heads = e->NKV;
-      r = launch_attention_tc<act_t>(maps, ap, n_works, e->NKV, e->DH, st, e->attn_version);
+      r = e->attn_version == kAttnWarpSpecialized ? launch_attention_ws<act_t>(e->tm_q, maps, ap, n_works, e->NKV, e->DH, st)
+                                                   : launch_attention_tc<act_t>(maps, ap, n_works, e->NKV, e->DH, st, e->attn_version);
     }
     e->toc(st);
     if (r != cudaSuccess) return e->fail_cuda("attention launch", r);
