@@ -472,8 +472,17 @@ def run_workload(args, wl, topk_override, cfg, model, dev, rank, world, local_ra
     flops0 = eng.gemm_flops()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    if distributed:
+        model.shard_timing = {}
     total_ms, (res, plan) = timed(step_device, args.steps)
     clocks = sampler.stop()
+    rank_busy = None
+    if distributed and model.shard_timing.get("t1") is not None:   # last step: this rank's own scoring, before the single all-gather
+        own = torch.tensor([model.shard_timing["t0"].elapsed_time(model.shard_timing["t1"])], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(own) for _ in range(world)]
+        dist.all_gather(allr, own)
+        rank_busy = [round(float(x.item()), 1) for x in allr]
+        model.shard_timing = None
     detail = eng.profile_read_detail()
     prof = eng.profile_read()
     eng.profile(False)
@@ -557,7 +566,8 @@ def run_workload(args, wl, topk_override, cfg, model, dev, rank, world, local_ra
                            "unique_vtg_pairs": int(plan.union_key.numel()), "alpha": alpha, "c": c,
                            "precision": DTYPE_NOTE,
                            "l2": "no flush needed: every step streams 15 GB of weights per decoder run (>> 126 MB L2)",
-                           "parallelism": f"pairs sharded by prefix owner over {world} GPU(s), weights replicated"},
+                           "parallelism": f"pairs sharded by prefix owner over {world} GPU(s), weights replicated",
+                           "rank_scoring_ms_last_step": rank_busy},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "rank_parity": rank_parity, "reference_gpu": reference_gpu, "recall_blim": res}
         print(json.dumps(line), flush=True)

@@ -204,6 +204,7 @@ class Engine:
 
     def set_tvg_prefix_length(self, n):
         self._check(self.lib.blim_set_tvg_prefix_length(self.h, int(n)))
+        self.tvg_prefix_length = int(n)
 
     # ---------------------------------------------------------------- scoring
     def score_pairs(self, kind, pair_v, pair_t, out=None):

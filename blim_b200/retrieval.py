@@ -131,22 +131,39 @@ class PairPlan:
         self.t2v_np = (packed[2 * nu + 2 * na:2 * nu + 2 * na + nb], packed[2 * nu + 2 * na + nb:])
 
 
+LM_ROW_COST = 0.084   # one LM-head row in units of one decoder token (2*H*V / 13.05 GFLOP at 7B; a few % either way elsewhere)
+
+
 def _shard_costs(eng, kind, pv, pt):
-    """(owner type, owner ids, per-pair suffix tokens, per-owner prefix tokens) for the scheduler's four run shapes
-    (csrc/engine.cu).  Owner = the id whose shared prefix the pairs hang off: "v" (video) or "t" (text)."""
+    """(owner type, owner ids, per-pair cost, per-owner cost) in decoder-token equivalents for the scheduler's four run
+    shapes (csrc/engine.cu), i.e. what the rank that owns the prefix will actually execute after the engine's own
+    deduplication.  Owner = the id whose shared prefix the pairs hang off: "v" (video) or "t" (text)."""
     lens = getattr(eng, "text_lens", None)
     if not lens or TEXTS_VTG not in lens or TEXTS_TVG not in lens:
         lens = None
     n_vis = getattr(eng, "n_clips", 4) * 64
-    cap = lens[TEXTS_VTG]["scored"] if lens else None
-    tlen = lens[TEXTS_TVG]["total"] if lens else None
-    if kind == VTG:          # owner = video: prefix (header + visual rows + prompt) once, one caption suffix per pair
-        return "v", pv, (cap[pt] if lens else np.full(len(pv), 14.0)), n_vis + 26.0
-    if kind == VTG_PRIOR:    # owner = text: one suffix per distinct text, the 26-token prefix is shared by everyone
-        return "t", pt, (cap[pt] / 16.0 if lens else np.ones(len(pt))), 0.0
-    if kind == TVG:          # owner = text: text prefix once, n_clips - 1 visual rows per pair
-        return "t", pt, np.full(len(pt), 3.0), (tlen if lens else 45.0)
-    return "v", pv, np.full(len(pv), 4.0), 0.0   # TVG_PRIOR, owner = video
+    n_clips = getattr(eng, "n_clips", 4)
+    root = getattr(eng, "tvg_prefix_length", 21)
+    if lens:
+        scored = lens[TEXTS_VTG]["scored"]                     # caption + <|im_end|> + "\n": LM rows of a pair
+        suffix = (scored - 1.0) + LM_ROW_COST * scored          # decoder tokens of the suffix sequence + its LM rows
+        t0 = lens[TEXTS_TVG]["total"] - 3.0                    # text part of the TVG prompt
+    if kind == VTG:          # owner = video: [visual rows + prompt tail] once (the header is a shared root), one caption suffix per pair
+        return "v", pv, (suffix[pt] if lens else np.full(len(pv), 15.0)), n_vis + 12.0
+    if kind == VTG_PRIOR:    # owner = text: ONE suffix per distinct text however many videos list it; the 26-token prefix is shared
+        per_text = np.zeros(int(pt.max()) + 1 if len(pt) else 0)
+        if len(pt):
+            per_text[np.unique(pt)] = suffix[np.unique(pt)] if lens else 15.0
+        return "t", pt, np.zeros(len(pt)), per_text
+    if kind == TVG:          # owner = text: its text prefix behind the shared root once, n_clips - 1 visual rows per pair
+        return "t", pt, np.full(len(pt), n_clips - 1.0), (np.maximum(t0 - root, 1.0) if lens else 25.0)
+    # TVG_PRIOR, owner = video: one n_clips-token suffix per distinct text length among the video's pairs (the engine dedupes
+    # on (header, T0, last token, video))
+    per_video = np.zeros(int(pv.max()) + 1 if len(pv) else 0)
+    if len(pv):
+        key = np.unique(pv.astype(np.int64) * 65536 + (t0[pt].astype(np.int64) if lens else 0))
+        per_video += np.bincount(key // 65536, minlength=len(per_video)) * float(n_clips)
+    return "v", pv, np.zeros(len(pv)), per_video
 
 
 def balanced_owner_ranks(costs, world):
@@ -154,14 +171,15 @@ def balanced_owner_ranks(costs, world):
     summed over ALL score kinds of the evaluation: videos and texts go into one list, largest first, each to the currently
     lightest rank (LPT).  The ranks meet once, at the single all-gather, so only the total per rank matters.
     Deterministic: every rank derives the same assignment from the plan.  Returns {"v": rank_of_video, "t": rank_of_text}."""
+    import heapq
     items = [(float(c), typ, i) for typ in ("v", "t") for i, c in enumerate(costs.get(typ, ())) if c > 0]
     items.sort(key=lambda x: (-x[0], x[1], x[2]))
-    load = np.zeros(world)
+    heap = [(0.0, r) for r in range(world)]          # (load, rank): ties go to the lowest rank, like argmin
     rank_of = {typ: np.zeros(len(costs.get(typ, ())), dtype=np.int64) for typ in ("v", "t")}
     for c, typ, i in items:
-        r = int(np.argmin(load))
+        load, r = heapq.heappop(heap)
         rank_of[typ][i] = r
-        load[r] += c
+        heapq.heappush(heap, (load + c, r))
     return rank_of
 
 
@@ -176,8 +194,10 @@ class ShardPlan:
             typ, owner, pair_cost, base = _shard_costs(eng, kind, pv, pt)
             n_owner = len(costs[typ])
             c = np.bincount(owner, weights=pair_cost, minlength=n_owner).astype(np.float64)
-            base = base[:n_owner] if isinstance(base, np.ndarray) else base
-            costs[typ] += c + np.where(c > 0, base, 0.0)
+            used = np.bincount(owner, minlength=n_owner) > 0
+            if isinstance(base, np.ndarray):
+                base = np.pad(base, (0, max(0, n_owner - len(base))))[:n_owner]
+            costs[typ] += c + np.where(used, base, 0.0)
             owners[name] = (typ, owner)
         rank_of = balanced_owner_ranks(costs, world)
         self.shards = {}                      # name -> [pair indices of rank r]
@@ -222,11 +242,18 @@ def score_all(model, plan: PairPlan, cpn=True, full=True, distributed=False):
         return {name: eng.score_pairs(kind, pv, pt) for name, kind, pv, pt in jobs}
     sp = ShardPlan(eng, jobs, world, plan.n_videos, plan.n_texts)
     send = torch.zeros(sp.width, dtype=torch.float32, device=eng.device)
+    timing = getattr(m, "shard_timing", None)      # bench.py: device time of this rank's own scoring, before the ranks meet
+    if timing is not None:
+        timing["t0"] = torch.cuda.Event(enable_timing=True)
+        timing["t0"].record()
     for name, kind, pv, pt in jobs:
         mine = sp.shards[name][rank]
         if len(mine):
             off = int(sp.offsets[name][rank])
             eng.score_pairs(kind, pv[mine], pt[mine], out=send[off:off + len(mine)])
+    if timing is not None:
+        timing["t1"] = torch.cuda.Event(enable_timing=True)
+        timing["t1"].record()
     if hasattr(eng, "allgather_scores"):
         eng.comm_init()                        # first call only: joins the engine's NCCL communicator
         gathered = eng.allgather_scores(send)
