@@ -129,11 +129,22 @@ class BlimModel:
             if torch.is_tensor(video):
                 feats = video
             else:
-                # per-video async H2D copies into one device tensor (no 0.5 GB host-side torch.stack)
+                # H2D into one device tensor (no 0.5 GB host-side torch.stack): ONE copy when the list is a run of consecutive
+                # views of a single host buffer (what a loader over a pre-stacked / pinned feature tensor yields), else one
+                # async copy per video
                 video = list(video)
                 feats = torch.empty((len(video),) + tuple(video[0].shape), dtype=video[0].dtype, device=self.device)
-                for i, v in enumerate(video):
-                    feats[i].copy_(v, non_blocking=True)
+                v0 = video[0]
+                step = v0.numel() * v0.element_size()
+                whole = (v0.device.type == "cpu" and v0.is_contiguous()
+                         and all(v.dtype == v0.dtype and v.shape == v0.shape and v.is_contiguous() and v.data_ptr() == v0.data_ptr() + i * step
+                                 and v.untyped_storage().data_ptr() == v0.untyped_storage().data_ptr() for i, v in enumerate(video)))
+                if whole:
+                    flat = torch.as_strided(v0, (len(video),) + tuple(v0.shape), (v0.numel(),) + tuple(v0.stride()))
+                    feats.copy_(flat, non_blocking=True)
+                else:
+                    for i, v in enumerate(video):
+                        feats[i].copy_(v, non_blocking=True)
             self.engine.set_videos(feats)
             self._corpus_keys["video"] = key
             self._corpus_keys.pop("vocab", None)
