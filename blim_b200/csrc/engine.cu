@@ -162,6 +162,7 @@ struct blim_engine {
   DevBuf d_tok_slot, d_tok_src, d_tok_pos, d_key_valid, d_seqs, d_works, d_idx, d_targets, d_row_off, d_map, d_seq_start;
   int ksplit = 1, nsplit = 0;             // K slices of the long-K residual GEMM (1 = off) / N slices of gate|up (0 = by weight size)
   size_t ksplit_min_bytes = 100u << 20;   // weights larger than this are K-sliced
+  int resid_tma = 0;                      // BLIM_RESID_TMA=1|2: residual add of o_proj (| and down_proj) through a TMA reduce (EpiResidTma)
   int nsplit_min_rows = 20000;            // gate|up is only N-sliced for runs of at least this many rows: below, A fits the L2 next
                                           // to the streaming weights and the slices only add wave quantisation (BLIM_GEMM_NSPLIT_MIN_ROWS)
   int attn_version = kAttnWarpSpecialized;  // BLIM_ATTN=tc2p|tc2: the round-1 kernels (A/B against the warp-specialised default)
@@ -234,6 +235,7 @@ template <class Epi> struct EpiProf { static int sub(const blim_engine*, int) { 
 template <int D> struct EpiProf<EpiQkvRope<D>> { static int sub(const blim_engine*, int) { return kProfQkv; } };
 template <> struct EpiProf<EpiSwiglu> { static int sub(const blim_engine*, int) { return kProfGateUp; } };
 template <> struct EpiProf<EpiLse> { static int sub(const blim_engine*, int) { return kProfLse; } };
+template <> struct EpiProf<EpiResidTma> { static int sub(const blim_engine* e, int K) { return K == e->NQ ? kProfOProj : kProfDown; } };
 template <int G> struct EpiProf<EpiResidT<G>> { static int sub(const blim_engine* e, int K) { return K == e->NQ ? kProfOProj : kProfDown; } };   // down_proj may be K-sliced
 template <> struct EpiProf<EpiResidNorm> { static int sub(const blim_engine* e, int K) { return K == e->NQ ? kProfOProj : kProfDown; } };
 
@@ -326,6 +328,7 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
   e->gemm.cta_group = cfg->gemm_cta_group == 1 ? 1 : 2;  // default: CTA pairs (cta_group::2)
   if (const char* v = getenv("BLIM_GEMM_KSPLIT")) e->ksplit = std::max(1, std::min(8, atoi(v)));
   if (const char* v = getenv("BLIM_GEMM_NSPLIT")) e->nsplit = std::max(1, std::min(16, atoi(v)));
+  if (const char* v = getenv("BLIM_RESID_TMA")) e->resid_tma = std::max(0, std::min(2, atoi(v)));
   if (const char* v = getenv("BLIM_GEMM_NSPLIT_MIN_ROWS")) e->nsplit_min_rows = std::max(1, atoi(v));
   if (const char* h = getenv("BLIM_GEMM_HINTS")) e->gemm.l2_hints = atoi(h) != 0;
   if (const char* m = getenv("BLIM_GEMM_SB_MB")) { e->gemm.sb_mb = std::max(4, std::min(96, atoi(m))); e->gemm.sb_auto = false; }
@@ -734,6 +737,12 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
       rstd_rows_kernel<<<(R + 255) / 256, 256, 0, st>>>(e->rstd.as<float>(), e->ssq.as<float>(), R, n_parts, e->H, e->cfg.rms_norm_eps);
       CKL();
       return 0;
+    }
+    if (e->resid_tma && (e->H % 32) == 0 && (e->resid_tma == 2 || K == e->NQ)) {   // 1: o_proj only (short K), 2: down_proj too
+      EpiResidTma::Params pt;
+      if (!make_tmap_f32_32x32(&pt.tm_x, x, static_cast<uint64_t>(R), static_cast<uint64_t>(e->H), static_cast<uint64_t>(e->H)))
+        return e->fail("cuTensorMapEncodeTiled failed for the residual stream");
+      return gemm<EpiResidTma>(e, A, lda, W, lda, R, e->H, K, pt, st);
     }
     EpiResid::Params pr{x, e->H};
     // A/B knob (BLIM_GEMM_KSPLIT, default 1 = off): cut a long-K contraction (down_proj, 136 MB of weights) into K slices,

@@ -41,8 +41,11 @@ struct GemmCfg {
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kOutStageBytes = 8 * 32 * 80;  // per epilogue warp: 32 rows x (64 B + 16 B pad) for coalesced bf16 stores
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kOutStageBytes + 1024;
+  // per epilogue warp a 4 KB slab, 1024-byte aligned: 32 rows x (64 B + 16 B pad) for the coalesced 16-bit / fp32 stores, or a
+  // 128-byte-swizzled 32 x 32 fp32 tile that a TMA reduce adds to the residual stream (EpiResidTma)
+  static constexpr int kOutWarpBytes = 4096;
+  static constexpr int kOutStageBytes = 8 * kOutWarpBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutStageBytes + kBarBytes + 1024;
 };
 
 struct GemmDims {
@@ -255,6 +258,46 @@ struct EpiResidT {
 
 using EpiResid = EpiResidT<2>;
 
+// A/B variant (BLIM_RESID_TMA=1|2, off by default): resid[row, col] += acc through the TMA -- the warp's 32 x 32 fp32 piece
+// is written to its shared-memory slab (128-byte swizzle) and ONE cp.reduce.async.bulk.tensor (.add, fp32) hands it to
+// the L2, which performs the read-modify-write, so the epilogue warps never wait for residual rows to arrive.  Every
+// element receives exactly one add per GEMM: the same IEEE sum as the in-register version (the GPU tests pass with it).
+// Measured on the same box (profiles/r02_bench_c2_ab_epilogues_same_box_v22.log): o_proj 393-396 -> 399 ms per C2 step, i.e.
+// no gain -- with the staged read-modify-write the epilogue already hides under the next tile's mainloop, so the in-register
+// version stays the default.  Needs N % 32 == 0; rows beyond M are clipped by the tensor map.
+struct EpiResidTma {
+  static constexpr int kGroups = 2;
+  struct Params {
+    CUtensorMap tm_x;   // fp32 [M, N] residual stream, box = 32 columns x 32 rows, SWIZZLE_128B
+  };
+  __device__ static void run(const Params& p, const GemmDims& d, int row, int n0, int n_tile, uint32_t taddr, int half, uint8_t* wstage) {
+    const int lane = threadIdx.x & 31;
+    const int r0 = row - lane;
+#pragma unroll 1
+    for (int c = half * (kBN / 2); c < (half + 1) * (kBN / 2); c += 32) {
+      float v[32];
+      tmem_ld32f(taddr + c, v);
+      const int col = n0 + c;
+      if (col >= d.N) continue;   // warp-uniform
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous reduce has read the slab
+      __syncwarp();
+      float4* srow = reinterpret_cast<float4*>(wstage + lane * 128);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) srow[i ^ (lane & 7)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && r0 < d.M) {
+        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(&p.tm_x)), "r"(smem_u32(wstage)), "r"(col), "r"(r0)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the slab outlives every read of it
+    __syncwarp();
+  }
+};
+
 // resid[row, col] += acc + bias[col]   (ViT blocks: attn.proj / mlp.fc2 carry a bias, vision_tower_builder.py:96,53)
 struct EpiResidBias {
   static constexpr int kGroups = 2;
@@ -407,6 +450,8 @@ struct EpiQkvRope {
         lo[i] = rope ? a * cs[i] - b * sn[i] : a;
         hi[i] = rope ? b * cs[i] + a * sn[i] : b;
       }
+      // (staging these rows through shared memory like the other epilogues, with vector bias loads, measured 2 % SLOWER on
+      // the same box: per-row destinations need a shuffle per piece, and the rotary math, not the stores, bounds this epilogue)
       if (row_ok) {
         store_row32_16<act_t>(dst + j0, lo, 32);
         store_row32_16<act_t>(dst + kHalf + j0, hi, 32);
@@ -505,13 +550,14 @@ struct EpiLse {
 template <class Epi, int kCtaGroup>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDims dims,
-                    const typename Epi::Params ep) {
+                    const __grid_constant__ typename Epi::Params ep) {   // grid constant: an epilogue may hold a tensor map (EpiResidTma)
   using Cfg = GemmCfg<kCtaGroup>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* s_a = smem;
   uint8_t* s_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* s_out = smem + Cfg::kStages * Cfg::kStageBytes;   // epilogue staging slabs (1024-byte aligned)
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_out + Cfg::kOutStageBytes);
   uint64_t* bar_empty = bar_full + Cfg::kStages;
   uint64_t* bar_tfull = bar_empty + Cfg::kStages;
   uint64_t* bar_tempty = bar_tfull + 2;
@@ -620,7 +666,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBN);
-      Epi::run(ep, dims, row, n_tile * kBN, n_tile, taddr, half, smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + (warp - 4) * (32 * 80));
+      Epi::run(ep, dims, row, n_tile * kBN, n_tile, taddr, half, s_out + (warp - 4) * Cfg::kOutWarpBytes);
       tc_fence_before();
       if (is_leader) mbar_arrive(&bar_tempty[acc]); else mbar_arrive_cluster(&bar_tempty[acc], 0);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -663,6 +709,19 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, ui
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// fp32 row-major [rows, cols] matrix; box = 32 columns x 32 rows, 128 B swizzle (EpiResidTma)
+inline bool make_tmap_f32_32x32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
