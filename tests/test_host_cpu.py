@@ -140,13 +140,14 @@ def test_committed_ncu_launch_list_reproduces_the_share_summary(tmp_path):
     import json
     import subprocess
     import sys
-    lists = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_ncu_launches_c2_n96_v1?.csv")))
+    lists = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0?_ncu_launches_c2_n96_v??.csv")))      # latest round, latest version
     assert lists, "no committed ncu launch list"
     out = str(tmp_path / "shares.json")
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), "shares", out, lists[-1]], check=True)
     got = json.load(open(out))
+    rnd = os.path.basename(lists[-1]).split("_", 1)[0]
     tag = lists[-1].rsplit("_", 1)[1].split(".")[0]
-    want = json.load(open(os.path.join(ROOT, "profiles", f"r01_ncu_launch_shares_{tag}.json")))
+    want = json.load(open(os.path.join(ROOT, "profiles", f"{rnd}_ncu_launch_shares_{tag}.json")))
     assert [k["kernel"] for k in got["kernels"][:6]] == [k["kernel"] for k in want["kernels"][:6]]
     assert abs(got["total_ms"] - want["total_ms"]) < 1e-6
     gemm = sum(k["share_pct"] for k in got["kernels"] if k["kernel"].startswith("gemm_tcgen05_kernel"))
@@ -168,6 +169,30 @@ def test_balanced_owner_ranks_lpt():
         assert load.max() - load.min() <= max(costs["v"].max(), costs["t"].max())
         naive = sum(np.bincount(np.arange(len(costs[k])) % world, weights=costs[k], minlength=world) for k in ("v", "t"))
         assert load.max() <= naive.max() + 1e-9          # never worse than the round-robin it replaces
+
+
+def test_shard_costs_model_what_a_rank_executes():
+    """Owner costs in decoder-token equivalents after the engine's own deduplication: a VTG-prior text costs ONE suffix however
+    many videos list it, a TVG text its prefix behind the shared root, a TVG-prior video one suffix per distinct text length."""
+    from blim_b200.retrieval import LM_ROW_COST, _shard_costs
+    from blim_b200.engine import TEXTS_TVG, TEXTS_VTG, TVG, TVG_PRIOR, VTG, VTG_PRIOR
+
+    class E:
+        n_clips = 4
+        tvg_prefix_length = 21
+        text_lens = {TEXTS_VTG: {"total": np.array([40.0, 45.0, 50.0]), "scored": np.array([12.0, 17.0, 22.0])},
+                     TEXTS_TVG: {"total": np.array([50.0, 55.0, 55.0]), "scored": np.array([3.0, 3.0, 3.0])}}
+    pv = np.array([0, 0, 1, 1, 2])
+    pt = np.array([0, 1, 1, 2, 1])
+    suffix = lambda s: (s - 1.0) + LM_ROW_COST * s
+    typ, owner, pair, base = _shard_costs(E, VTG, pv, pt)
+    assert typ == "v" and np.array_equal(owner, pv) and np.allclose(pair, [suffix(12), suffix(17), suffix(17), suffix(22), suffix(17)]) and base == 268.0
+    typ, owner, pair, base = _shard_costs(E, VTG_PRIOR, pv, pt)
+    assert typ == "t" and not pair.any() and np.allclose(base, [suffix(12), suffix(17), suffix(22)])      # text 1 listed by 3 videos: once
+    typ, owner, pair, base = _shard_costs(E, TVG, pv, pt)
+    assert typ == "t" and np.allclose(pair, 3.0) and np.allclose(base, [47 - 21, 52 - 21, 52 - 21])
+    typ, owner, pair, base = _shard_costs(E, TVG_PRIOR, pv, pt)
+    assert typ == "v" and not pair.any() and np.allclose(base, [8.0, 4.0, 4.0])     # video 0: two text lengths, video 1: texts 1 and 2 share T0
 
 
 def test_shard_plan_layout():
