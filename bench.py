@@ -13,7 +13,7 @@ VideoChat-Flash-Qwen2-7B (random init), MSRVTT-1k shape (1000 queries x top-16),
                                                              same reference timed on one B200 through PyTorch is reported
                                                              beside it as `reference_gpu`
 N > 1: launched by torchrun, one rank per GPU; pairs are sharded by prefix owner (strong scaling of the fixed job),
-one NCCL all-gather of compact scores per score kind.
+ONE NCCL all-gather of compact scores per step, issued by the engine on its compute stream.
 """
 import argparse
 import contextlib

@@ -1,20 +1,22 @@
-// tcgen05 / TMEM attention: varlen causal GQA with a shared (cascade) prefix segment -- the tensor-core version of
-// attention.cuh (same semantics, same AttnSeq description; reference: Qwen2SdpaAttention, modeling_qwen2_flash.py:685-709).
+// tcgen05 / TMEM attention: varlen causal GQA with a shared (cascade) prefix segment (sequence description: attention.cuh;
+// reference semantics: Qwen2SdpaAttention, modeling_qwen2_flash.py:685-709).  This header holds the kernels in which one
+// group of threads executes the whole per-chunk chain -- used by the feature extractor (attention_tc4_kernel at head_dim
+// 64, attention_tc2_kernel otherwise) and as the A/B fallback of the scoring path (BLIM_ATTN=tc2p|tc2) -- plus the work
+// list builder and the tensor-map / launch helpers.  The scoring path's default is the warp-specialised kernel in
+// attention_ws.cuh, which shares the work items, masks and numerics described here.
 //
 // One CTA = up to 128 stacked query rows (row = token * G + head-in-group of `128 / G` consecutive tokens of a
-// prefix-sharing group of sequences) x one KV head; one thread per row.
-//   S  = Q K^T      tcgen05.mma  M=128, N=16..64 (keys of the chunk), K=head_dim          -> TMEM columns [0, 64)
+// prefix-sharing group of sequences) x one KV head.
+//   S  = Q K^T      tcgen05.mma  M=128, N=16..64 (keys of the chunk), K=head_dim          -> TMEM
 //   softmax         each thread reads ITS row of S from TMEM (tcgen05.ld 32x32b): running max / sum / rescale are
-//                   thread-local, no shuffles; P (bf16) goes to a 128-byte-swizzled K-major tile in shared memory
-//   Oc = P V        tcgen05.mma  M=128, N=head_dim, K=keys; V stays [key][head_dim] in memory = MN-major B operand
-//                   (descriptor semantics pinned by tests/test_umma_probe_gpu.py)                -> TMEM columns [64, 64+head_dim)
-//   O  = O * corr + Oc   accumulated in registers (fp32), normalised and written as bf16 at the end.
+//                   thread-local; P (16-bit operand format) goes to a 128-byte-swizzled K-major tile in shared memory
+//   O += P V        tcgen05.mma  M=128, N=head_dim, K=keys; V stays [key][head_dim] in memory = MN-major B operand
+//                   (descriptor semantics pinned by tests/test_umma_probe_gpu.py); O lives in TMEM
 // Keys come in 64-key chunks: first the a_len prefix keys (all visible), then ONE contiguous range of own-run keys
 // [first token of the first sequence in the block, last token of the block]: key kt is visible to the query at token rt
 // iff seq_start(rt) <= kt <= rt and key_valid[kt] -- sequences are contiguous in the run, so "same sequence AND causal"
-// is an interval test.  K / V chunks are staged by TMA (64 keys x 64 columns boxes, SWIZZLE_128B, mbarrier completion):
-// K for chunk c+1 is in flight while the softmax of chunk c runs, V for c+1 while O is accumulated; two CTAs per SM
-// overlap each other's phases.  Rows of a box beyond the chunk's keys hold other (finite) cache rows and meet P = 0.
+// is an interval test.  K / V chunks are staged by TMA (64 keys x 64 columns boxes, SWIZZLE_128B, mbarrier completion).
+// Rows of a box beyond the chunk's keys hold other (finite) cache rows and meet P = 0.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -57,16 +59,13 @@ struct AttnParamsTc {
 };
 
 constexpr int kTcKeys = 64;       // keys per chunk
-constexpr int kTcThreads = 128;
 constexpr int kTcTmemCols = 256;  // S (64) + Oc (<= 128), power of two
 
 // ------------------------------------------------------------------------------------------------ v2: O stays in TMEM
-// Same decomposition, deeper overlap (the production kernel; the one above is kept for A/B runs, BLIM_ATTN=tc1):
 //   * 256 threads: two threads per query row (warps w and w+4 share a TMEM lane quadrant); each handles 32 of the chunk's
 //     64 keys and half of the head_dim columns, the row maximum is exchanged through shared memory;
 //   * O is accumulated by the tensor core in TMEM (Oc = P V with accumulate); it is only touched by threads when the
-//     running reference maximum has to grow by more than 2^8 ("lazy rescale": tcgen05.ld -> scale -> tcgen05.st), so the
-//     per-chunk register traffic of the first kernel (128 TMEM->register FMAs per row) disappears;
+//     running reference maximum has to grow by more than 2^8 ("lazy rescale": tcgen05.ld -> scale -> tcgen05.st);
 //   * S = Q K^T of chunk c+1 is issued right behind Oc = P V of chunk c, so it runs under the softmax of nobody and is
 //     ready when the threads come back; V is double-buffered, K single-buffered, both by TMA.
 constexpr int kTc2Threads = 256;
@@ -644,14 +643,9 @@ attention_tc2p_kernel(const __grid_constant__ CUtensorMap tm_ka, const __grid_co
   if (warp == 0) tmem_dealloc<1>(tmem, kTcTmemCols);
 }
 
-// ------------------------------------------------------------------------------------------------ v3: S and K double-buffered
-// Same as v2, plus: two S accumulators in TMEM and two K stages in shared memory, so S = Q K^T of chunk c+1 is issued at
-// the TOP of round c (its K chunk was prefetched a whole round earlier) and runs under the softmax of chunk c; at the end
-// of a round only Oc = P V is issued.  All bookkeeping lives in dynamic shared memory (no static __shared__) so that two
-// CTAs of 112.6 KB still fit one SM; the host checks the occupancy and falls back to v2 otherwise.
 // ------------------------------------------------------------------------------------------------ v4: dedicated issue warp
-// Same data flow as v3 (two S accumulators in TMEM, K and V double-buffered), but every TMA and tcgen05.mma is issued by a
-// NINTH warp that does nothing else.  In v2 / v3 thread 0 issues them between its own softmax work, so warp 0 executes
+// Two S accumulators in TMEM, K and V double-buffered, and every TMA and tcgen05.mma is issued by a
+// NINTH warp that does nothing else.  In v2 thread 0 issues them between its own softmax work, so warp 0 executes
 // ~2x the instructions of the other warps and the whole CTA waits for it at every __syncthreads: the per-chunk critical
 // path was warp 0's instruction stream (ncu: 42 % issue utilisation, 17 % tensor pipe on the ViT shapes).  Here the
 // 256 softmax threads only talk to the issue warp through mbarriers:

@@ -165,7 +165,6 @@ struct blim_engine {
   int resid_tma = 0;                      // BLIM_RESID_TMA=1|2: residual add of o_proj (| and down_proj) through a TMA reduce (EpiResidTma)
   int nsplit_min_rows = 20000;            // gate|up is only N-sliced for runs of at least this many rows: below, A fits the L2 next
                                           // to the streaming weights and the slices only add wave quantisation (BLIM_GEMM_NSPLIT_MIN_ROWS)
-  int attn_tpr = 1;                          // BLIM_ATTN=ws2: two softmax threads per row (attention_tc6_kernel)
   int attn_version = kAttnWarpSpecialized;  // BLIM_ATTN=tc2p|tc2: the round-1 kernels (A/B against the warp-specialised default)
   CUtensorMap tm_q;                          // e->q as a (head_dim, head, token) tensor: Q tiles by TMA (attention_ws.cuh)
   uint8_t* arena = nullptr;  // pinned staging arena for scheduler metadata (see upload())
@@ -320,7 +319,6 @@ extern "C" int blim_create(const blim_model_cfg* cfg, int device, blim_engine** 
   e->gemm.device = device;
   {
     const char* a = getenv("BLIM_ATTN");
-    e->attn_tpr = (a && std::string(a) == "ws2") ? 2 : 1;
     e->attn_version = (a && std::string(a) == "tc2") ? kAttnPerItem : (a && std::string(a) == "tc2p") ? kAttnPersistent : kAttnWarpSpecialized;
     const char* rs = getenv("BLIM_ROOT");
     e->root_share = !(rs && std::string(rs) == "0");
@@ -804,7 +802,7 @@ static int run_decoder(blim_engine* e, Run& run, bool to_prefix_cache, bool asse
       ap.key_valid = run.any_invalid ? e->d_key_valid.as<uint8_t>() : nullptr;
       ap.tok_seq_start = e->d_seq_start.as<int>(); ap.works = e->d_works.as<AttnWorkTc>();
       ap.n_q = e->NQ; ap.n_kv = e->NKVD; ap.group = e->G; ap.scale_log2 = scale_log2; ap.q_stride = e->NQ; ap.n_works = n_works; ap.n_kv_heads = e->NKV;
-      r = e->attn_version == kAttnWarpSpecialized ? launch_attention_ws<act_t>(e->tm_q, maps, ap, n_works, e->NKV, e->DH, st, e->attn_tpr)
+      r = e->attn_version == kAttnWarpSpecialized ? launch_attention_ws<act_t>(e->tm_q, maps, ap, n_works, e->NKV, e->DH, st)
                                                    : launch_attention_tc<act_t>(maps, ap, n_works, e->NKV, e->DH, st, e->attn_version);
     }
     e->toc(st);
