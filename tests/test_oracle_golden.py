@@ -68,3 +68,37 @@ def test_reference_invariants(case):
         both = (x != -100.0) & (y != -100.0)
         assert both.sum() > 0
         assert np.abs(x[both] - y[both]).max() < 2e-5
+
+
+def test_reference_runner_reproduces_goldens_and_rank_parity_helpers():
+    """oracle/ref_gpu.py (the driver of the UNMODIFIED reference used as comparator at 7B and by bench.py) on the CPU: its
+    matrices are the goldens bit for bit, the fused rows equal the goldens' BLiM matrices, and rank_parity reports a perfect
+    match of a result with itself and a swap when two close candidates are exchanged."""
+    from oracle import ref_gpu, ref_harness
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree not present")
+    from oracle.make_golden import CASES, build_case
+    case = CASES["tiny_a"]
+    cfg, w, corpus = build_case(case)
+    g = np.load(os.path.join(GOLDEN, "tiny_a.npz"))
+    rr = ref_gpu.ReferenceRunner(cfg, {k: v.float() for k, v in w.items()}, corpus, "cpu", dtype=torch.float32)
+    mats, secs, pairs = rr.all_matrices(0, corpus.n, case["topk"], case["bs"])
+    assert pairs == 2 * corpus.n * case["topk"]
+    key = {"v2t_candidate_likelihood": "v2t_vtg_lik", "v2t_candidate_prior": "v2t_vtg_cpn", "v2t_query_likelihood": "v2t_tvg_lik",
+           "t2v_query_likelihood": "t2v_vtg_lik", "t2v_candidate_likelihood": "t2v_tvg_lik", "t2v_candidate_prior": "t2v_tvg_cpn"}
+    for name, (idx, sc) in mats.items():
+        assert np.array_equal(np.take_along_axis(g[key[name]], idx, 1), sc), name
+    f = ref_gpu.fused_rows(mats, corpus, 0, corpus.n, case["alpha"], case["c"])
+    assert np.array_equal(f["t2v"][0], g["blim_t2v"]) and np.array_equal(f["v2t"][0], g["blim_v2t"])
+    same = ref_gpu.rank_parity(f, f)
+    for d in ("t2v", "v2t"):
+        assert same[d]["rows_same_order"] == corpus.n and same[d]["recall_equal"] and same[d]["swapped_adjacent_pairs"] == 0
+    # exchange the scores of the two best candidates of row 0 in one matrix: exactly that row's order changes
+    swapped = {k: (i.copy(), s.copy()) for k, (i, s) in mats.items()}
+    o = f["t2v"][1][0]                                         # candidate ids of row 0, best first
+    idx, sc = swapped["t2v_query_likelihood"]
+    a, b = int(np.where(idx[0] == o[0])[0][0]), int(np.where(idx[0] == o[1])[0][0])
+    sc[0, a], sc[0, b] = sc[0, b] - 1.0, sc[0, a] + 1.0        # push them past each other
+    f2 = ref_gpu.fused_rows(swapped, corpus, 0, corpus.n, case["alpha"], case["c"])
+    rp = ref_gpu.rank_parity(f, f2)
+    assert rp["t2v"]["rows_same_order"] == corpus.n - 1 and rp["t2v"]["swapped_adjacent_pairs"] >= 1 and rp["v2t"]["rows_same_order"] == corpus.n
