@@ -73,6 +73,15 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------ helpers
+def shared_config(wl, n, topk, world):
+    """The `config` object of BOTH arms (the driver compares them): what is being measured, nothing arm-specific."""
+    return {"workload": wl["desc"], "n_queries": int(n), "topk": int(topk), "pairs_per_step": int(2 * n * topk), "matrices": 6,
+            "alpha": list(wl["alpha"]), "c": list(wl["c"]),
+            "l2": "no flush needed: every step streams 15 GB of weights per decoder run (>> 126 MB L2)",
+            "parallelism": f"pairs sharded by prefix owner over {world} GPU(s), weights replicated"}
+
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -313,7 +322,7 @@ def run_reference_arm(args, wl, rank, world):
     pairs = 2 * CPU_SAMPLE_PAIRS
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * pairs / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": {"workload": wl["desc"]},
+            "data": "synthetic", "config": shared_config(wl, args.n or wl["n"] or synth.DATASET_SHAPES[wl["dataset"]]["n"], args.topk or wl["topk"], args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "reference_gpu": reference_gpu}
@@ -562,12 +571,8 @@ def run_workload(args, wl, topk_override, cfg, model, dev, rank, world, local_ra
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE,
                 "data": "synthetic",
-                "config": {"workload": wl["desc"], "n_queries": n, "topk": topk, "pairs_per_step": pairs, "matrices": 6,
-                           "unique_vtg_pairs": int(plan.union_key.numel()), "alpha": alpha, "c": c,
-                           "precision": DTYPE_NOTE,
-                           "l2": "no flush needed: every step streams 15 GB of weights per decoder run (>> 126 MB L2)",
-                           "parallelism": f"pairs sharded by prefix owner over {world} GPU(s), weights replicated",
-                           "rank_scoring_ms_last_step": rank_busy},
+                "config": shared_config(wl, n, topk, world),
+                "engine": {"precision": DTYPE_NOTE, "unique_vtg_pairs": int(plan.union_key.numel()), "rank_scoring_ms_last_step": rank_busy},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "rank_parity": rank_parity, "reference_gpu": reference_gpu, "recall_blim": res}
         print(json.dumps(line), flush=True)
