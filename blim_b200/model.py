@@ -16,6 +16,50 @@ IGNORE_INDEX = -100
 IMAGE_TOKEN_INDEX = -200
 
 
+def upload_videos(video, device, shard=None):
+    """Host feature list / tensor -> ONE device tensor [n, n_clips, tokens, mm].  No host-side torch.stack: a list that is a
+    run of consecutive views of a single host buffer (what a loader over a pre-stacked / pinned feature tensor yields) goes
+    in one copy, anything else in one async copy per video.  With shard = (rank, world), world > 1, only videos
+    [rank * per, (rank + 1) * per), per = ceil(n / world), are copied from the host; torch.distributed all-gathers the
+    slices into the full tensor on the devices."""
+    if torch.is_tensor(video):
+        n, v0 = video.shape[0], video[0]
+        get = lambda lo, hi: video[lo:hi]
+        whole = True
+    else:
+        video = list(video)
+        n, v0 = len(video), video[0]
+        step = v0.numel() * v0.element_size()
+        whole = (v0.device.type == "cpu" and v0.is_contiguous()
+                 and all(v.dtype == v0.dtype and v.shape == v0.shape and v.is_contiguous() and v.data_ptr() == v0.data_ptr() + i * step
+                         and v.untyped_storage().data_ptr() == v0.untyped_storage().data_ptr() for i, v in enumerate(video)))
+        flat = torch.as_strided(v0, (n,) + tuple(v0.shape), (v0.numel(),) + tuple(v0.stride())) if whole else None
+        get = (lambda lo, hi: flat[lo:hi]) if whole else None
+
+    def copy_into(dst, lo, hi):           # dst[:hi - lo] <- videos lo..hi-1
+        if hi <= lo:
+            return
+        if whole:
+            dst[:hi - lo].copy_(get(lo, hi), non_blocking=True)
+        else:
+            for i in range(lo, hi):
+                dst[i - lo].copy_(video[i], non_blocking=True)
+
+    shape = tuple(v0.shape)
+    rank, world = shard if shard else (0, 1)
+    if world <= 1:
+        feats = torch.empty((n,) + shape, dtype=v0.dtype, device=device)
+        copy_into(feats, 0, n)
+        return feats
+    import torch.distributed as dist
+    per = (n + world - 1) // world
+    mine = torch.zeros((per,) + shape, dtype=v0.dtype, device=device)
+    copy_into(mine, min(n, rank * per), min(n, (rank + 1) * per))
+    full = torch.empty((per * world,) + shape, dtype=v0.dtype, device=device)
+    dist.all_gather_into_tensor(full, mine)
+    return full[:n]
+
+
 class BlimModel:
     def __init__(self, cfg: ModelConfig, state_dict=None, device=0, **engine_kw):
         self.config = cfg
@@ -123,28 +167,14 @@ class BlimModel:
         ends = [t for t in (x[0], x[-1])] if x else []
         return ("l", len(x)) + tuple((t.data_ptr(), tuple(t.shape), str(t.dtype), t._version) if torch.is_tensor(t) else id(t) for t in ends)
 
-    def ensure_videos(self, video):
+    def ensure_videos(self, video, shard=None):
+        """Feature list / tensor -> engine.  shard = (rank, world) of an initialised process group: every rank holds the same
+        host copy of the corpus (like every rank of the reference loads the whole loader, retrieval_utils.py:182-193), so each
+        uploads only its 1/world slice over PCIe and the slices are all-gathered device to device (NVLink) instead of every
+        rank pulling all 0.5 GB through its host link."""
         key = ("video", self._tensors_key(video))
         if self._corpus_keys.get("video") != key:
-            if torch.is_tensor(video):
-                feats = video
-            else:
-                # H2D into one device tensor (no 0.5 GB host-side torch.stack): ONE copy when the list is a run of consecutive
-                # views of a single host buffer (what a loader over a pre-stacked / pinned feature tensor yields), else one
-                # async copy per video
-                video = list(video)
-                feats = torch.empty((len(video),) + tuple(video[0].shape), dtype=video[0].dtype, device=self.device)
-                v0 = video[0]
-                step = v0.numel() * v0.element_size()
-                whole = (v0.device.type == "cpu" and v0.is_contiguous()
-                         and all(v.dtype == v0.dtype and v.shape == v0.shape and v.is_contiguous() and v.data_ptr() == v0.data_ptr() + i * step
-                                 and v.untyped_storage().data_ptr() == v0.untyped_storage().data_ptr() for i, v in enumerate(video)))
-                if whole:
-                    flat = torch.as_strided(v0, (len(video),) + tuple(v0.shape), (v0.numel(),) + tuple(v0.stride()))
-                    feats.copy_(flat, non_blocking=True)
-                else:
-                    for i, v in enumerate(video):
-                        feats[i].copy_(v, non_blocking=True)
+            feats = video if torch.is_tensor(video) and video.device.type == "cuda" else upload_videos(video, self.device, shard)
             self.engine.set_videos(feats)
             self._corpus_keys["video"] = key
             self._corpus_keys.pop("vocab", None)

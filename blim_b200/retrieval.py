@@ -328,7 +328,7 @@ def evaluation(model, data_loader, device, tokenizer, args):
 
     # pad-stripped ragged texts go straight to the engine (padding_ids + the mask strip of mvf:333-334 cancel out)
     if staged is None:
-        m.ensure_videos(video)
+        m.ensure_videos(video, shard=_world() if getattr(args, "distributed", False) else None)
         eng.set_texts(TEXTS_VTG, vtg_ids, vtg_labels, vtg_masks)
         eng.set_texts(TEXTS_TVG, tvg_ids, tvg_labels, tvg_masks)
         if full:

@@ -238,3 +238,30 @@ def test_algorithmic_flops_matches_survey_order_of_magnitude():
     plan = PairPlan(c.v2t_iv2, c.t2v_iv2, 16, "cpu")
     g, a = bench.algorithmic_flops(cfg, c, plan)
     assert 8e15 < g + a < 2e16, (g, a)
+
+
+def _upload_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from blim_b200.model import upload_videos
+    g = torch.Generator().manual_seed(0)
+    big = torch.randn(7, 2, 4, 8, generator=g).half()                 # 7 videos: not a multiple of the world size
+    res = {}
+    for name, video in (("views", [big[i] for i in range(7)]), ("separate", [big[i].clone() for i in range(7)]), ("tensor", big)):
+        res[name] = upload_videos(video, torch.device("cpu"), (rank, world)).clone()
+    if rank == 1:
+        torch.save({"big": big, **res}, out)
+    dist.destroy_process_group()
+
+
+def test_sharded_feature_upload_over_two_ranks(tmp_path):
+    """Multi-GPU e2e path: every rank copies only its slice of the corpus from the host and the slices are all-gathered --
+    the result is the whole corpus on every rank, whatever form the loader's video list has."""
+    from blim_b200.model import upload_videos
+    out = str(tmp_path / "up.pt")
+    mp.spawn(_upload_worker, args=(2, 29500 + (os.getpid() % 2000) + 7, out), nprocs=2, join=True)
+    got = torch.load(out)
+    for name in ("views", "separate", "tensor"):
+        assert torch.equal(got[name], got["big"]), name
+    one = upload_videos([got["big"][i] for i in range(7)], torch.device("cpu"))      # single process: plain copy
+    assert torch.equal(one, got["big"])
