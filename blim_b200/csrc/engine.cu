@@ -887,6 +887,13 @@ static int plan_batches(blim_engine* e, const std::vector<UnitPlan>& units, cons
     const UnitPlan& up = units[u];
     if (up.prefix_len > e->Pmax || up.prefix_len > e->Tmax) return e->fail("a prefix sequence exceeds the workspace (raise max_prefix_tokens / max_run_tokens)");
     size_t pos = 0;
+    // A unit's items stay in ONE batch whenever they fit an empty one: the attention tiles of a unit stack its sequences in
+    // run order, so cutting a unit at a batch boundary that depends on what else is being scored would move its tile (and
+    // 64-key chunk) boundaries -- the scores must not depend on the batch composition / the multi-GPU sharding.
+    long long unit_s = 0;
+    for (int it : up.items) unit_s += items[it].suf_len;
+    const bool fits_alone = unit_s <= scap && static_cast<long long>(up.items.size()) <= max_items;
+    if (fits_alone && !cur.empty() && (cs + unit_s > scap || ci + static_cast<long long>(up.items.size()) > max_items)) flush();
     while (pos < up.items.size()) {
       const int first_len = items[up.items[pos]].suf_len;
       if (first_len > e->Tmax) return e->fail("a suffix sequence exceeds max_run_tokens");
