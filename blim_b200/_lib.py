@@ -92,6 +92,7 @@ SIGNATURES = {
     "blim_profile": (c_int, [c_void_p, c_int]),
     "blim_profile_read": (c_int, [c_void_p, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "blim_profile_read_detail": (c_int, [c_void_p, c_int, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), ctypes.POINTER(c_i64)]),
+    "blim_debug_plan_batches": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "blim_debug_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_uint32, ctypes.c_uint32,
                                 ctypes.c_uint32, c_void_p]),
     "blim_debug_gemm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -860,56 +860,82 @@ struct BatchUnit {
   int item_begin, item_end;  // range inside units[unit].items
 };
 
-static int plan_batches(blim_engine* e, const std::vector<UnitPlan>& units, const std::vector<Item>& items, int max_items,
-                        std::vector<std::vector<BatchUnit>>& batches, int reserve_rows = 0) {
+// Pure host code (no engine, no device): blim_debug_plan_batches runs it on a described workload in the CPU tests.
+struct PlanCaps {
+  int Pmax, Tmax, Umax;  // prefix-cache rows, run tokens, prefix units per run
+};
+static const char* plan_batches_host(const PlanCaps* e, const std::vector<UnitPlan>& units, const std::vector<Item>& items, int max_items,
+                                     std::vector<std::vector<BatchUnit>>& batches, int reserve_rows) {
   batches.clear();
-  std::vector<BatchUnit> cur;
   const int pcap_hard = std::min(e->Pmax, e->Tmax) - reserve_rows;  // a prefix run is also one decoder run; root rows come first
-  if (pcap_hard <= 0) return e->fail("workspace too small for the shared prompt header");
+  if (pcap_hard <= 0) return "workspace too small for the shared prompt header";
   // balance: n batches of roughly equal size instead of (n-1) full ones and a small tail (small runs waste the GEMMs)
   long long tot_p = 0, tot_s = 0, tot_i = 0;
-  int max_p = 0, max_s = 0;
+  int max_p = 0;
+  long long max_s = 0;  // slack of the balanced suffix capacity: the largest piece that is placed whole (a unit, see below)
   for (const UnitPlan& up : units) {
     tot_p += up.prefix_len;
     max_p = std::max(max_p, up.prefix_len);
-    for (int it : up.items) { tot_s += items[it].suf_len; max_s = std::max(max_s, items[it].suf_len); ++tot_i; }
-  }
-  long long nb = std::max<long long>(1, std::max((tot_p + pcap_hard - 1) / pcap_hard, std::max((tot_s + e->Tmax - 1) / e->Tmax, (tot_i + max_items - 1) / max_items)));
-  const int pcap = static_cast<int>(std::min<long long>(pcap_hard, (tot_p + nb - 1) / nb + max_p));
-  const int scap = static_cast<int>(std::min<long long>(e->Tmax, (tot_s + nb - 1) / nb + max_s));
-  long long cp = 0, cs = 0;
-  int ci = 0;
-  auto flush = [&]() {
-    if (!cur.empty()) batches.push_back(cur);
-    cur.clear(); cp = 0; cs = 0; ci = 0;
-  };
-  for (size_t u = 0; u < units.size(); ++u) {
-    const UnitPlan& up = units[u];
-    if (up.prefix_len > e->Pmax || up.prefix_len > e->Tmax) return e->fail("a prefix sequence exceeds the workspace (raise max_prefix_tokens / max_run_tokens)");
-    size_t pos = 0;
-    // A unit's items stay in ONE batch whenever they fit an empty one: the attention tiles of a unit stack its sequences in
-    // run order, so cutting a unit at a batch boundary that depends on what else is being scored would move its tile (and
-    // 64-key chunk) boundaries -- the scores must not depend on the batch composition / the multi-GPU sharding.
     long long unit_s = 0;
-    for (int it : up.items) unit_s += items[it].suf_len;
-    const bool fits_alone = unit_s <= scap && static_cast<long long>(up.items.size()) <= max_items;
-    if (fits_alone && !cur.empty() && (cs + unit_s > scap || ci + static_cast<long long>(up.items.size()) > max_items)) flush();
-    while (pos < up.items.size()) {
-      const int first_len = items[up.items[pos]].suf_len;
-      if (first_len > e->Tmax) return e->fail("a suffix sequence exceeds max_run_tokens");
-      if (cp + up.prefix_len > pcap || static_cast<int>(cur.size()) + 1 > e->Umax || cs + first_len > scap || ci + 1 > max_items) flush();
-      BatchUnit bu{static_cast<int>(u), static_cast<int>(pos), static_cast<int>(pos)};
-      cp += up.prefix_len;
-      while (pos < up.items.size() && cs + items[up.items[pos]].suf_len <= scap && ci + 1 <= max_items) {
-        cs += items[up.items[pos]].suf_len;
-        ++ci; ++pos;
-      }
-      bu.item_end = static_cast<int>(pos);
-      cur.push_back(bu);
-    }
+    for (int it : up.items) { unit_s += items[it].suf_len; max_s = std::max<long long>(max_s, items[it].suf_len); ++tot_i; }
+    tot_s += unit_s;
+    if (unit_s <= e->Tmax && static_cast<long long>(up.items.size()) <= max_items) max_s = std::max(max_s, unit_s);
   }
-  flush();
-  return 0;
+  for (const UnitPlan& up : units)
+    if (up.prefix_len > e->Pmax || up.prefix_len > e->Tmax) return "a prefix sequence exceeds the workspace (raise max_prefix_tokens / max_run_tokens)";
+  for (const Item& it : items)
+    if (it.suf_len > e->Tmax) return "a suffix sequence exceeds max_run_tokens";
+  // greedy placement in run order for a target of nb batches: capacities = the average + the largest piece placed whole,
+  // so every batch but the last holds at least the average
+  auto place = [&](long long nb) {
+    batches.clear();
+    std::vector<BatchUnit> cur;
+    const int pcap = static_cast<int>(std::min<long long>(pcap_hard, (tot_p + nb - 1) / nb + max_p));
+    const int scap = static_cast<int>(std::min<long long>(e->Tmax, (tot_s + nb - 1) / nb + max_s));
+    long long cp = 0, cs = 0;
+    int ci = 0;
+    auto flush = [&]() {
+      if (!cur.empty()) batches.push_back(cur);
+      cur.clear(); cp = 0; cs = 0; ci = 0;
+    };
+    for (size_t u = 0; u < units.size(); ++u) {
+      const UnitPlan& up = units[u];
+      size_t pos = 0;
+      // A unit's items stay in ONE batch whenever they fit an empty one: the attention tiles of a unit stack its sequences
+      // in run order, so cutting a unit at a batch boundary that depends on what else is being scored would move its tile
+      // (and 64-key chunk) boundaries -- the scores must not depend on the batch composition / the multi-GPU sharding.
+      long long unit_s = 0;
+      for (int it : up.items) unit_s += items[it].suf_len;
+      const bool fits_alone = unit_s <= scap && static_cast<long long>(up.items.size()) <= max_items;
+      if (fits_alone && !cur.empty() && (cs + unit_s > scap || ci + static_cast<long long>(up.items.size()) > max_items)) flush();
+      while (pos < up.items.size()) {
+        const int first_len = items[up.items[pos]].suf_len;   // <= scap: the slack covers the longest sequence
+        if (cp + up.prefix_len > pcap || static_cast<int>(cur.size()) + 1 > e->Umax || cs + first_len > scap || ci + 1 > max_items) flush();
+        BatchUnit bu{static_cast<int>(u), static_cast<int>(pos), static_cast<int>(pos)};
+        cp += up.prefix_len;
+        while (pos < up.items.size() && cs + items[up.items[pos]].suf_len <= scap && ci + 1 <= max_items) {
+          cs += items[up.items[pos]].suf_len;
+          ++ci; ++pos;
+        }
+        bu.item_end = static_cast<int>(pos);
+        cur.push_back(bu);
+      }
+    }
+    flush();
+  };
+  // (Re-planning for the number of batches this really took -- equal runs instead of full ones and a small tail -- was
+  // tried: with two balanced capacities, prefix rows and suffix tokens, closing a batch on one leaves it short of the
+  // average of the other, and the TVG runs of C2 went from 3 batches to 5.  A tail run costs ~5 ms of a 7 s job; left alone.)
+  const long long nb = std::max<long long>(1, std::max((tot_p + pcap_hard - 1) / pcap_hard, std::max((tot_s + e->Tmax - 1) / e->Tmax, (tot_i + max_items - 1) / max_items)));
+  place(nb);
+  return nullptr;
+}
+
+static int plan_batches(blim_engine* e, const std::vector<UnitPlan>& units, const std::vector<Item>& items, int max_items,
+                        std::vector<std::vector<BatchUnit>>& batches, int reserve_rows = 0) {
+  const PlanCaps caps{e->Pmax, e->Tmax, e->Umax};
+  const char* err = plan_batches_host(&caps, units, items, max_items, batches, reserve_rows);
+  return err ? e->fail(err) : 0;
 }
 
 // ------------------------------------------------------------------------------------------------ TVG pooled visual rows
@@ -1690,6 +1716,31 @@ extern "C" int blim_debug_gemm(blim_engine* e, int epilogue, const void* A, cons
   }
   e->gemm.cta_group = saved;
   return r;
+}
+
+// Host-only view of the batch planner (no engine, no device): which batch each suffix sequence of a described workload
+// lands in.  The CPU tests pin the planner's contract with it -- capacities respected, and a unit's sequences never cut
+// at a batch boundary unless the unit alone exceeds a run (what keeps the scores independent of batching / sharding).
+extern "C" int blim_debug_plan_batches(int max_prefix_tokens, int max_run_tokens, int max_units, int max_items, int reserve_rows,
+                                       const int32_t* unit_prefix_len, const int32_t* unit_item_count, int n_units,
+                                       const int32_t* item_suf_len, int32_t* batch_of_item_out) {
+  if (!unit_prefix_len || !unit_item_count || !item_suf_len || !batch_of_item_out || n_units < 0 || max_items <= 0 || max_run_tokens <= 0) return -1;
+  std::vector<UnitPlan> units(static_cast<size_t>(n_units));
+  std::vector<Item> items;
+  for (int u = 0; u < n_units; ++u) {
+    units[u].prefix_len = unit_prefix_len[u];
+    for (int j = 0; j < unit_item_count[u]; ++j) {
+      units[u].items.push_back(static_cast<int>(items.size()));
+      items.push_back(Item{u, item_suf_len[items.size()], static_cast<int>(items.size())});
+    }
+  }
+  const PlanCaps caps{max_prefix_tokens, max_run_tokens, max_units};
+  std::vector<std::vector<BatchUnit>> batches;
+  if (plan_batches_host(&caps, units, items, max_items, batches, reserve_rows)) return -1;
+  for (size_t b = 0; b < batches.size(); ++b)
+    for (const BatchUnit& bu : batches[b])
+      for (int j = bu.item_begin; j < bu.item_end; ++j) batch_of_item_out[units[bu.unit].items[j]] = static_cast<int32_t>(b);
+  return static_cast<int>(batches.size());
 }
 
 extern "C" int blim_debug_umma(blim_engine* e, const void* A, const void* B, float* C, int K, int N, int b_mn_major, uint32_t lbo, uint32_t sbo,

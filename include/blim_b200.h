@@ -180,6 +180,18 @@ int blim_debug_gemm(blim_engine* e, int epilogue, const void* A, const void* W, 
 int blim_debug_umma(blim_engine* e, const void* A, const void* B, float* C, int K, int N, int b_mn_major, uint32_t lbo, uint32_t sbo,
                     uint32_t kstep_bytes, void* stream);
 
+/* Debug / unit-test entry, HOST ONLY (needs neither an engine nor a device): the batch planner blim_score_pairs uses to
+ * cut a scoring job into decoder runs, on a described workload.  Unit u (one shared prefix: a video with its captions, a
+ * text with its candidate videos) has unit_prefix_len[u] prefix tokens and unit_item_count[u] suffix sequences whose
+ * lengths follow each other in item_suf_len, unit after unit.  Capacities as in the model configuration struct: max_prefix_tokens,
+ * max_run_tokens; max_units prefixes and max_items suffix sequences per batch, reserve_rows cache rows kept for the
+ * shared prompt header.  Writes the batch index of every suffix sequence and returns the number of batches, -1 when the
+ * workload does not fit.  Contract (tests/test_host_cpu.py): capacities hold, order is preserved, and a unit that fits
+ * a batch on its own is never split -- the precondition for scores that do not depend on the sharding. */
+int blim_debug_plan_batches(int max_prefix_tokens, int max_run_tokens, int max_units, int max_items, int reserve_rows,
+                            const int32_t* unit_prefix_len, const int32_t* unit_item_count, int n_units,
+                            const int32_t* item_suf_len, int32_t* batch_of_item_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -265,3 +265,83 @@ def test_sharded_feature_upload_over_two_ranks(tmp_path):
         assert torch.equal(got[name], got["big"]), name
     one = upload_videos([got["big"][i] for i in range(7)], torch.device("cpu"))      # single process: plain copy
     assert torch.equal(one, got["big"])
+
+
+# ------------------------------------------------------------------------------------------------ batch planner (host only)
+def _plan_batches(pmax, tmax, umax, max_items, reserve, prefix_len, item_lens):
+    """blim_debug_plan_batches on units given as (prefix_len[u], [suffix lengths of unit u])."""
+    import ctypes
+    from blim_b200 import _lib
+    lib = _lib.load()
+    counts = np.asarray([len(x) for x in item_lens], np.int32)
+    flat = np.asarray([v for x in item_lens for v in x] or [0], np.int32)
+    pre = np.asarray(prefix_len, np.int32)
+    out = np.full(max(1, int(counts.sum())), -1, np.int32)
+    nb = lib.blim_debug_plan_batches(pmax, tmax, umax, max_items, reserve, pre.ctypes.data_as(ctypes.c_void_p),
+                                     counts.ctypes.data_as(ctypes.c_void_p), len(item_lens),
+                                     flat.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p))
+    return nb, out[:int(counts.sum())]
+
+
+def _check_plan(pmax, tmax, umax, max_items, reserve, prefix_len, item_lens):
+    nb, batch = _plan_batches(pmax, tmax, umax, max_items, reserve, prefix_len, item_lens)
+    assert nb >= 1 and (batch >= 0).all() and batch.max() == nb - 1
+    assert (np.diff(batch) >= 0).all()                       # run order is kept: batches are consecutive ranges of the job
+    unit_of = np.repeat(np.arange(len(item_lens)), [len(x) for x in item_lens])
+    lens = np.asarray([v for x in item_lens for v in x])
+    split = []
+    for b in range(nb):
+        sel = batch == b
+        assert lens[sel].sum() <= tmax and sel.sum() <= max_items
+        units = np.unique(unit_of[sel])
+        assert len(units) <= umax
+        assert sum(prefix_len[u] for u in units) <= min(pmax, tmax) - reserve
+    for u, x in enumerate(item_lens):
+        if len(np.unique(batch[unit_of == u])) > 1:
+            split.append(u)
+    return nb, batch, split
+
+
+def test_batch_planner_never_cuts_a_unit_that_fits():
+    """The sharding invariance of the scores rests on this: whatever else is in the job, the suffix
+    sequences of one prefix (a video's captions, a text's candidates) run in ONE batch, so their attention tiles and
+    64-key chunks fall on the same boundaries at every world size."""
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        n_units = int(rng.integers(1, 80))
+        tmax = int(rng.choice([2048, 4096, 49152]))
+        pmax = int(rng.choice([2048, 4096, 49152]))
+        max_items = int(rng.choice([64, tmax // 2]))
+        prefix_len = [int(rng.integers(20, 300)) for _ in range(n_units)]
+        item_lens = [[int(v) for v in rng.integers(1, 40, size=int(rng.integers(1, 33)))] for _ in range(n_units)]
+        nb, batch, split = _check_plan(pmax, tmax, 8192, max_items, 14, prefix_len, item_lens)
+        assert not split, (trial, split)                      # every unit here fits a batch on its own
+        # any shard (subset of the units, as a rank of a multi-GPU job sees it) keeps every unit whole as well
+        keep = sorted(rng.choice(n_units, size=max(1, n_units // 3), replace=False).tolist())
+        _, _, split = _check_plan(pmax, tmax, 8192, max_items, 14, [prefix_len[u] for u in keep], [item_lens[u] for u in keep])
+        assert not split
+
+
+def test_batch_planner_capacities_and_oversized_units():
+    # a unit larger than a run is the one case that may be cut; everything still respects the capacities
+    nb, batch, split = _check_plan(4096, 1024, 8192, 512, 0, [100, 100, 100], [[30] * 10, [40] * 60, [30] * 10])
+    assert split == [1] and nb >= 3
+    # items cap: 5 units x 8 sequences, at most 16 sequences per batch -> two units per batch, none split
+    nb, batch, split = _check_plan(4096, 4096, 8192, 16, 0, [50] * 5, [[5] * 8] * 5)
+    assert nb == 3 and not split
+    # prefix-row cap decides: 200-token prefixes, 512 cache rows of which 14 are the shared header -> two units per batch
+    nb, batch, split = _check_plan(512, 4096, 8192, 2048, 14, [200] * 6, [[5] * 4] * 6)
+    assert nb == 3 and not split
+    # unit cap
+    nb, batch, split = _check_plan(4096, 4096, 2, 2048, 0, [10] * 6, [[5] * 2] * 6)
+    assert nb == 3 and not split
+    # single batch when everything fits; a sequence longer than a run / a prefix longer than the cache are refused
+    nb, batch, _ = _check_plan(49152, 49152, 8192, 24576, 14, [282] * 125, [[20] * 16] * 125)
+    assert nb == 1
+    # the balanced capacity (average + the largest piece placed whole) evens the runs out: 20 units of 500 tokens in
+    # 4 700-token runs -> 7 + 7 + 6 units, not 9 + 9 + 2
+    nb, batch, split = _check_plan(49152, 4700, 8192, 2048, 0, [100] * 20, [[100] * 5] * 20)
+    assert nb == 3 and not split and np.bincount(batch).tolist() == [35, 35, 30]
+    assert _plan_batches(4096, 1024, 8192, 512, 0, [10], [[2000]])[0] == -1
+    assert _plan_batches(256, 4096, 8192, 512, 0, [300], [[5]])[0] == -1
+    assert _plan_batches(4096, 4096, 8192, 512, 4096, [10], [[5]])[0] == -1
