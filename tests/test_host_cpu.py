@@ -345,3 +345,33 @@ def test_batch_planner_capacities_and_oversized_units():
     assert _plan_batches(4096, 1024, 8192, 512, 0, [10], [[2000]])[0] == -1
     assert _plan_batches(256, 4096, 8192, 512, 0, [300], [[5]])[0] == -1
     assert _plan_batches(4096, 4096, 8192, 512, 4096, [10], [[5]])[0] == -1
+
+
+def test_a_rank_of_an_8_gpu_c2_job_runs_every_kind_as_one_batch():
+    """with 49 152-token workspaces a rank's share of the C2 job is ONE prefix run + ONE suffix run per score
+    kind, and the shards are even in decoder tokens.  Checked with the engine's own planner on the real ShardPlan."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("plan_batches_tool", os.path.join(ROOT, "tools", "plan_batches.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    from blim_b200 import retrieval, synth
+    from blim_b200.engine import TVG, TVG_PRIOR, VTG, VTG_PRIOR, ModelConfig
+    cfg = ModelConfig.qwen2_7b()
+    cfg.mm_hidden_size = 8
+    corpus = synth.make_corpus(cfg, "msrvtt", seed=1)
+    lens = tool._Lens(corpus)
+    pp = retrieval.PairPlan(corpus.v2t_iv2, corpus.t2v_iv2, 16, "cpu")
+    jobs = [("vtg", VTG) + tuple(pp.union_np), ("vtg_prior", VTG_PRIOR) + tuple(pp.v2t_np),
+            ("tvg", TVG) + tuple(pp.union_np), ("tvg_prior", TVG_PRIOR) + tuple(pp.t2v_np)]
+    sp = retrieval.ShardPlan(lens, jobs, 8, pp.n_videos, pp.n_texts)
+    totals = []
+    for r in range(8):
+        total = 0
+        for name, kind, pv, pt in jobs:
+            sel = sp.shards[name][r]
+            pre, item_lens, div, reserve = tool.units_of(kind, pv[sel], pt[sel], corpus, lens)
+            suf, rows = tool.plan(49152, 49152, 49152 // div, reserve, pre, item_lens)
+            assert len(suf) == 1, (r, name, suf)
+            total += sum(suf) + sum(rows)
+        totals.append(total)
+    assert max(totals) <= 1.01 * np.mean(totals), totals
